@@ -1,0 +1,171 @@
+/*
+ * vgpa_b200.h -- C ABI of libvgpa_b200.so: the B200 (sm_100a) implementation of
+ * VGPA's variational free-energy + gradient evaluation for a BATCH of
+ * independent inference problems.
+ *
+ * The reference (vrettasm/VGPA) is pure Python and has no FFI; its boundary is
+ * the pair of callables handed to the SCG optimiser.  Each entry point below
+ * names the reference interface it stands in for (paths relative to the
+ * reference root).  Plain pointers and sizes only; all arrays are C-contiguous
+ * float64 in the reference's own layouts:
+ *
+ *     x    = [ A (N,D,D) | b (N,D) ]          (variational.py:153-162)
+ *     grad = [ dL/dA (N,D,D) | dL/db (N,D) ]  (variational.py:284-288)
+ *
+ * D = 1 (DW, OU) uses the same layout with 1x1 matrices.
+ *
+ * Scope: diagonal system noise Sigma, diagonal observation noise R, identity
+ * observation operator -- everything the sim_params JSON schema can express
+ * (vgpa_main.py:38-40, simulation.py:107-176).  L96 is built for D = 40
+ * (the only size simulation.py:20,134 can construct).
+ *
+ * Return codes (mapped to the exceptions the reference raises):
+ *     VGPA_OK            0
+ *     VGPA_EINVAL        1   -> ValueError
+ *     VGPA_ENOTPD        2   -> numpy.linalg.LinAlgError   (utilities.py:211,275:
+ *                               a covariance S(t) is not positive definite)
+ *     VGPA_ECUDA         3   -> RuntimeError
+ *
+ * Threading: one handle is driven by one host thread at a time (the
+ * reference's VarGP.output cache is equally non re-entrant); different
+ * handles / devices may run concurrently.  There is NO CPU fallback.
+ */
+#ifndef VGPA_B200_H
+#define VGPA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VGPA_OK = 0, VGPA_EINVAL = 1, VGPA_ENOTPD = 2, VGPA_ECUDA = 3 };
+
+/* simulation.py:20  dynamical_systems = {"DW","OU","L63","L96"} */
+enum { VGPA_MODEL_DW = 0, VGPA_MODEL_OU = 1, VGPA_MODEL_L63 = 2, VGPA_MODEL_L96 = 3 };
+/* utilities.py:12   num_integration = {"euler","heun","rk2","rk4"} */
+enum { VGPA_ODE_EULER = 0, VGPA_ODE_HEUN = 1, VGPA_ODE_RK2 = 2, VGPA_ODE_RK4 = 3 };
+
+typedef struct vgpa_handle vgpa_handle;
+
+/*
+ * Problem-batch descriptor.  Replaces the constructor arguments of
+ * VarGP(model, m0, s0, fwd_ode, bwd_ode, likelihood, kl0, obs_y, obs_t)
+ * (variational.py:15-71) together with the fields it reads from them:
+ * model.sigma / theta / time_step, likelihood.values / times / noise,
+ * fwd_ode.method / dt.  Host pointers; copied to the device by vgpa_create.
+ *
+ * Every per-problem array carries a stride in ELEMENTS between consecutive
+ * problems; stride 0 means "shared by all B problems".
+ */
+typedef struct {
+    int32_t model;   /* VGPA_MODEL_*                                              */
+    int32_t method;  /* VGPA_ODE_*                                                */
+    int32_t D;       /* state dimension (1, 3 or 40)                              */
+    int32_t N;       /* number of time-grid points = len(np.arange(t0,tf+dt,dt))  */
+    int32_t M;       /* number of observations                                    */
+    int32_t B;       /* number of independent problems in the batch               */
+    int32_t device;  /* CUDA device ordinal                                        */
+    int32_t reserved;
+    double dt;       /* step of the ODE sweeps (fwd_ode.py:14, JSON Time-window.dt) */
+    double dt_model; /* model.time_step (stochastic_process.py:117): trapezoid
+                        spacing (utilities.py:144) and gradient scale
+                        (variational.py:284-285)                                  */
+    const double *theta;  int64_t theta_stride;  /* DW/OU/L96: 1 value; L63: 3    */
+    const double *sigma;  int64_t sigma_stride;  /* D: diag of the system noise   */
+    const double *R;      int64_t R_stride;      /* D: diag of the obs. noise     */
+    const int64_t *obs_t;                        /* M sorted unique indices,
+                                                    shared by the batch
+                                                    (stochastic_process.py:166-175) */
+    const double *obs_y;  int64_t obs_y_stride;  /* M x D observation values      */
+    const double *m0;     int64_t m0_stride;     /* D                             */
+    const double *s0;     int64_t s0_stride;     /* D x D                         */
+    const double *E0;     int64_t E0_stride;     /* 1: prior KL at t=0, constant
+                                                    per problem (prior_kl0.py:30-92,
+                                                    variational.py:183-185)       */
+    int64_t scratch_bytes; /* device scratch budget for trajectories; 0 = default */
+} vgpa_desc;
+
+/* VarGP.__init__ (variational.py:15-71): validate, upload, allocate scratch. */
+int vgpa_create(const vgpa_desc *desc, vgpa_handle **out);
+void vgpa_destroy(vgpa_handle *h);
+/* Text of the last error on this handle (or of the last failed vgpa_create
+ * when h is NULL).  Valid until the next call on the handle. */
+const char *vgpa_last_error(const vgpa_handle *h);
+
+/*
+ * VarGP.free_energy(x) followed by VarGP.gradient(x) on the same x
+ * (variational.py:141-200 and :202-289), for all B problems.
+ *
+ * HOST buffers: x (B rows, x_stride elements apart; 0 = one x shared by all
+ * problems), F (B values), grad (B rows, grad_stride apart; may be NULL when
+ * want_grad == 0).  Host<->device copies are inside the call; pass memory from
+ * vgpa_host_alloc for full PCIe speed.
+ */
+int vgpa_eval(vgpa_handle *h, const double *x, int64_t x_stride, int want_grad,
+              double *F, double *grad, int64_t grad_stride);
+
+/*
+ * Same evaluation with DEVICE buffers on `stream` (a cudaStream_t passed as
+ * void*; NULL = default stream).  Asynchronous: returns after enqueueing.
+ * Call vgpa_sync to wait and to collect the positive-definiteness status.
+ */
+int vgpa_eval_device(vgpa_handle *h, const double *d_x, int64_t x_stride, int want_grad,
+                     double *d_F, double *d_grad, int64_t grad_stride, void *stream);
+int vgpa_sync(vgpa_handle *h);
+
+/*
+ * One problem, everything: F, its three parts, the gradient and every
+ * intermediate the reference caches in VarGP.output (variational.py:189-196,
+ * arg_out :292) or passes between its stages (:169-181).  HOST pointers; any
+ * output may be NULL.  x is that problem's own row (N*D*(D+1) values).
+ *   parts[3] = {E0, Esde, Eobs};  mt (N,D) st (N,D,D) lamt (N,D) psit (N,D,D)
+ *   Efx (N,D) Edf (N,D,D) dEsde_dm (N,D) dEsde_ds (N,D,D)
+ */
+typedef struct {
+    double *F, *parts, *grad;
+    double *mt, *st, *lamt, *psit, *Efx, *Edf, *dEsde_dm, *dEsde_ds;
+} vgpa_full_out;
+int vgpa_eval_full(vgpa_handle *h, int64_t problem, const double *x, const vgpa_full_out *out);
+
+/* The two sweeps on their own, as FwdOde.__call__ (fwd_ode.py:45) and
+ * BwdOde.__call__ (bwd_ode.py:45) expose them: one problem, HOST buffers.
+ *   fwd: A (N,D,D), b (N,D), m0 (D), s0 (D,D), sigma (D diag) -> mt, st
+ *   bwd: A, dEsde_dm (N,D), dEsde_ds (N,D,D), dEobs_dm (N,D), dEobs_ds (N,D,D)
+ *        -> lam (N,D), psi (N,D,D)
+ * (dense jump tables exactly as GaussianLikelihood.gradients returns them,
+ * gaussian_like.py:155-243; the jump added at each step is the one at t-1.) */
+int vgpa_solve_fwd(int device, int method, int D, int N, double dt, const double *A,
+                   const double *b, const double *m0, const double *s0, const double *sigma,
+                   double *mt, double *st);
+int vgpa_solve_bwd(int device, int method, int D, int N, double dt, const double *A,
+                   const double *dEsde_dm, const double *dEsde_ds, const double *dEobs_dm,
+                   const double *dEobs_ds, double *lam, double *psi);
+
+/* model.energy(A, b, m, S, obs_t) of a StochasticProcess subclass
+ * (double_well.py:169, ornstein_uhlenbeck.py:165, lorenz_63.py:237,
+ * lorenz_96.py:316): the time-parallel stage on its own, one problem, HOST
+ * buffers.  Outputs: Esde (1 value), Ef (N,D), Edf (N,D,D), dEsde_dm (N,D),
+ * dEsde_ds (N,D,D).  The hyper-parameter gradients dEsde_dtheta / dEsde_dsigma
+ * that the reference also returns are discarded by VarGP (variational.py:175)
+ * and are not computed. */
+int vgpa_model_energy(int device, int model, int D, int N, double dt_model, const double *theta,
+                      const double *sigma, const double *A, const double *b, const double *m,
+                      const double *S, double *Esde, double *Ef, double *Edf, double *dEsde_dm,
+                      double *dEsde_ds);
+
+/* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
+void *vgpa_host_alloc(int64_t bytes);
+void vgpa_host_free(void *p);
+
+/* Introspection for bench.py: kernels launched by the handle so far, the
+ * chunk size (problems resident per pass) and the scratch bytes in use. */
+int64_t vgpa_launch_count(const vgpa_handle *h);
+int64_t vgpa_chunk_size(const vgpa_handle *h);
+int64_t vgpa_scratch_in_use(const vgpa_handle *h);
+const char *vgpa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGPA_B200_H */

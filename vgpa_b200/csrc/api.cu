@@ -1,0 +1,648 @@
+// api.cu -- the C ABI of libvgpa_b200.so (include/vgpa_b200.h): handle management,
+// chunked three-phase evaluation (forward sweep -> time-parallel energy -> backward
+// sweep fused with the gradient), host staging with copy/compute overlap.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vgpa_b200.h"
+#include "common.cuh"
+
+using namespace vgpa;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t alloc(size_t n)
+    {
+        release();
+        if (n == 0) n = 8;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+int n_theta(int model) { return model == VGPA_MODEL_L63 ? 3 : 1; }
+
+}  // namespace
+
+struct vgpa_handle {
+    vgpa_desc d{};
+    Batch batch{};
+    Scratch scratch{};
+    int chunk = 0;
+    long long n_x = 0;   // N * D * (D + 1)
+    DevBuf theta, sigma, R, obs_t, obs_index, obs_y, m0, s0, E0, status;
+    DevBuf sc_mt, sc_st, sc_dEm, sc_dEs, sc_esde;
+    // host-API staging: two slots of one chunk each
+    DevBuf st_x[2], st_g[2], st_F;
+    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{};
+    cudaStream_t last_stream = nullptr;
+    bool status_dirty = false;
+    long long launches = 0;
+    std::string err;
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what)
+    {
+        return fail(VGPA_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define CK(call, what)                                         \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return h->cuda_fail(e__, what); \
+    } while (0)
+
+namespace {
+
+// upload a per-problem array given with an element stride (0 = shared)
+int upload(vgpa_handle* h, DevBuf& dst, const double* src, long long stride, long long len, int B,
+           const double** dev_ptr, long long* dev_stride, const char* name)
+{
+    if (src == nullptr) return h->fail(VGPA_EINVAL, "descriptor field %s is NULL", name);
+    if (stride != 0 && stride < len) return h->fail(VGPA_EINVAL, "%s_stride %lld < %lld", name, stride, len);
+    const long long copies = (stride == 0) ? 1 : B;
+    std::vector<double> host((size_t)copies * len);
+    for (long long q = 0; q < copies; ++q) memcpy(&host[(size_t)q * len], src + q * stride, sizeof(double) * len);
+    CK(dst.alloc(host.size() * sizeof(double)), "cudaMalloc(params)");
+    CK(cudaMemcpy(dst.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(params)");
+    *dev_ptr = dst.as<double>();
+    *dev_stride = (stride == 0) ? 0 : len;
+    return VGPA_OK;
+}
+
+bool small_model(int model) { return model != VGPA_MODEL_L96; }
+
+// one pass over problems [p0, p0 + count) with device buffers
+void run_chunk(vgpa_handle* h, const double* d_x, long long xs, int want_grad, double* d_F, double* d_grad,
+               long long gs, int p0, int count, const Extra& ex, cudaStream_t st)
+{
+    Scratch sc = h->scratch;
+    sc.status = h->status.as<int>() + p0;
+    const Batch& b = h->batch;
+    if (small_model(b.model)) {
+        launch_small_fwd(b, sc, d_x, xs, p0, count, st);
+        launch_small_energy(b, sc, d_x, xs, p0, count, ex, st);
+        launch_finalize(b, sc, d_F, p0, count, ex, st);
+        h->launches += 3;
+        if (want_grad) {
+            launch_small_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
+            h->launches += 1;
+        }
+    } else {
+        launch_l96_fwd(b, sc, d_x, xs, p0, count, st);
+        launch_l96_energy(b, sc, d_x, xs, p0, count, ex, st);
+        launch_finalize(b, sc, d_F, p0, count, ex, st);
+        h->launches += 3;
+        if (want_grad) {
+            launch_l96_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
+            h->launches += 1;
+        }
+    }
+}
+
+int check_status(vgpa_handle* h)
+{
+    if (!h->status_dirty) return VGPA_OK;
+    h->status_dirty = false;
+    std::vector<int> st(h->d.B);
+    CK(cudaMemcpy(st.data(), h->status.p, sizeof(int) * h->d.B, cudaMemcpyDeviceToHost), "cudaMemcpy(status)");
+    for (int p = 0; p < h->d.B; ++p)
+        if (st[p] != 0)
+            return h->fail(VGPA_ENOTPD, "Matrix is not positive definite: S(t) of problem %d at time index %d",
+                           p, st[p] - 1);
+    return VGPA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vgpa_version(void) { return "vgpa_b200 0.1 (sm_100a)"; }
+
+const char* vgpa_last_error(const vgpa_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vgpa_create(const vgpa_desc* d, vgpa_handle** out)
+{
+    if (out) *out = nullptr;
+    if (d == nullptr || out == nullptr) {
+        g_create_error = "vgpa_create: NULL argument";
+        return VGPA_EINVAL;
+    }
+    vgpa_handle* h = new vgpa_handle();
+    h->d = *d;
+    auto bail = [&](int rc) {
+        g_create_error = h->err;
+        vgpa_destroy(h);
+        return rc;
+    };
+    // ---- validation (the ValueErrors of the reference constructors) ----
+    if (d->model < 0 || d->model > 3) return bail(h->fail(VGPA_EINVAL, "Unknown stochastic model -> %d", d->model));
+    if (d->method < 0 || d->method > 3)
+        return bail(h->fail(VGPA_EINVAL, "Integration method is unknown -> %d", d->method));
+    const int needD = (d->model == VGPA_MODEL_L63) ? 3 : (d->model == VGPA_MODEL_L96 ? 40 : 1);
+    if (d->D != needD) return bail(h->fail(VGPA_EINVAL, "Wrong state dimension %d for model %d (need %d)", d->D, d->model, needD));
+    if (d->N < 2) return bail(h->fail(VGPA_EINVAL, "Need at least two time points, got %d", d->N));
+    if (d->M < 0 || d->B < 1) return bail(h->fail(VGPA_EINVAL, "Wrong sizes M=%d B=%d", d->M, d->B));
+    if (!(d->dt > 0.0) || !(d->dt_model > 0.0))
+        return bail(h->fail(VGPA_EINVAL, "Discrete time step should be strictly positive -> %g", d->dt));
+    if (d->M > 0 && d->obs_t == nullptr) return bail(h->fail(VGPA_EINVAL, "obs_t is NULL"));
+    for (int n = 0; n < d->M; ++n) {
+        if (d->obs_t[n] < 0 || d->obs_t[n] >= d->N || (n > 0 && d->obs_t[n] <= d->obs_t[n - 1]))
+            return bail(h->fail(VGPA_EINVAL, "obs_t must be sorted unique indices in [0, N)"));
+        // gaussian_like.py:137-146 indexes the covariance by the observation ordinal n
+        if (n >= d->N) return bail(h->fail(VGPA_EINVAL, "more observations than time points"));
+    }
+    {
+        const long long cnt = (d->sigma_stride == 0) ? 1 : d->B;
+        for (long long q = 0; d->sigma && q < cnt; ++q)
+            for (int i = 0; i < d->D; ++i)
+                if (!(d->sigma[q * d->sigma_stride + i] > 0.0))
+                    return bail(h->fail(VGPA_EINVAL, "The diffusion noise value should be strictly positive"));
+    }
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return bail(h->fail(VGPA_ECUDA, "cudaSetDevice(%d) failed: no usable CUDA device", d->device));
+    {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
+        if (e != cudaSuccess) return bail(h->cuda_fail(e, "cudaGetDeviceProperties"));
+        if (prop.major != 10)
+            return bail(h->fail(VGPA_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                                d->device, prop.major, prop.minor));
+    }
+    const int D = d->D, N = d->N, M = d->M, B = d->B;
+    h->n_x = (long long)N * D * (D + 1);
+    Batch& b = h->batch;
+    b.model = d->model; b.method = d->method; b.D = D; b.N = N; b.M = M; b.B = B;
+    b.dt = d->dt; b.dt_model = d->dt_model;
+    int rc;
+#define UP(field, len)                                                                              \
+    if ((rc = upload(h, h->field, d->field, d->field##_stride, (len), B, &b.field, &b.field##_stride, \
+                     #field)) != VGPA_OK)                                                           \
+        return bail(rc);
+    UP(theta, n_theta(d->model));
+    UP(sigma, D);
+    UP(R, D);
+    UP(m0, D);
+    UP(s0, (long long)D * D);
+    UP(E0, 1);
+    if (M > 0) {
+        UP(obs_y, (long long)M * D);
+    } else {
+        b.obs_y = nullptr;
+        b.obs_y_stride = 0;
+    }
+#undef UP
+    {
+        std::vector<long long> ot(std::max(M, 1), 0);
+        std::vector<int> oi(N, -1);
+        for (int n = 0; n < M; ++n) {
+            ot[n] = d->obs_t[n];
+            oi[d->obs_t[n]] = n;
+        }
+        cudaError_t e;
+        if ((e = h->obs_t.alloc(ot.size() * sizeof(long long))) != cudaSuccess ||
+            (e = h->obs_index.alloc(oi.size() * sizeof(int))) != cudaSuccess ||
+            (e = cudaMemcpy(h->obs_t.p, ot.data(), ot.size() * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(h->obs_index.p, oi.data(), oi.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(h->cuda_fail(e, "upload(obs_t)"));
+        b.obs_t = h->obs_t.as<long long>();
+        b.obs_index = h->obs_index.as<int>();
+    }
+    // ---- scratch: trajectories for one chunk of problems ----
+    const long long per = 8LL * N * (2LL * D + 2LL * D * D + 1);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    long long budget = d->scratch_bytes > 0 ? d->scratch_bytes : std::min<long long>(16LL << 30, (long long)(free_b * 0.35));
+    long long chunk = std::max<long long>(1, std::min<long long>(B, budget / per));
+    if (!small_model(d->model) && chunk >= 148) {
+        // whole waves: 3 forward CTAs / 2 backward CTAs fit per SM -> multiples of 6 * 148
+        const long long wave = 148 * 6;
+        if (chunk >= wave) chunk = (chunk / wave) * wave;
+        else chunk = (chunk / 148) * 148;
+    }
+    h->chunk = (int)chunk;
+    {
+        cudaError_t e;
+        if ((e = h->sc_mt.alloc(sizeof(double) * chunk * N * D)) != cudaSuccess ||
+            (e = h->sc_st.alloc(sizeof(double) * chunk * N * D * D)) != cudaSuccess ||
+            (e = h->sc_dEm.alloc(sizeof(double) * chunk * N * D)) != cudaSuccess ||
+            (e = h->sc_dEs.alloc(sizeof(double) * chunk * N * D * D)) != cudaSuccess ||
+            (e = h->sc_esde.alloc(sizeof(double) * chunk * N)) != cudaSuccess ||
+            (e = h->status.alloc(sizeof(int) * B)) != cudaSuccess ||
+            (e = cudaMemset(h->status.p, 0, sizeof(int) * B)) != cudaSuccess)
+            return bail(h->cuda_fail(e, "cudaMalloc(scratch)"));
+    }
+    h->scratch.mt = h->sc_mt.as<double>();
+    h->scratch.st = h->sc_st.as<double>();
+    h->scratch.dEm = h->sc_dEm.as<double>();
+    h->scratch.dEs = h->sc_dEs.as<double>();
+    h->scratch.esde_t = h->sc_esde.as<double>();
+    h->scratch.status = h->status.as<int>();
+    {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(h->cuda_fail(e, "cudaStreamCreate"));
+        for (int q = 0; q < 2; ++q)
+            if ((e = cudaEventCreateWithFlags(&h->ev_h2d[q], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_comp[q], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_d2h[q], cudaEventDisableTiming)) != cudaSuccess)
+                return bail(h->cuda_fail(e, "cudaEventCreate"));
+    }
+    *out = h;
+    return VGPA_OK;
+}
+
+void vgpa_destroy(vgpa_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->d.device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&h->theta, &h->sigma, &h->R, &h->obs_t, &h->obs_index, &h->obs_y, &h->m0, &h->s0, &h->E0,
+                      &h->status, &h->sc_mt, &h->sc_st, &h->sc_dEm, &h->sc_dEs, &h->sc_esde, &h->st_x[0],
+                      &h->st_x[1], &h->st_g[0], &h->st_g[1], &h->st_F})
+        b->release();
+    for (int q = 0; q < 2; ++q) {
+        if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
+        if (h->ev_comp[q]) cudaEventDestroy(h->ev_comp[q]);
+        if (h->ev_d2h[q]) cudaEventDestroy(h->ev_d2h[q]);
+    }
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int want_grad, double* d_F,
+                     double* d_grad, int64_t grad_stride, void* stream)
+{
+    if (!h) return VGPA_EINVAL;
+    if (d_x == nullptr || d_F == nullptr) return h->fail(VGPA_EINVAL, "x / F is NULL");
+    if (want_grad && d_grad == nullptr) return h->fail(VGPA_EINVAL, "want_grad set but grad is NULL");
+    if (x_stride != 0 && x_stride < h->n_x) return h->fail(VGPA_EINVAL, "x_stride %lld < %lld", (long long)x_stride, h->n_x);
+    if (want_grad && grad_stride < h->n_x && h->d.B > 1)
+        return h->fail(VGPA_EINVAL, "grad_stride %lld < %lld", (long long)grad_stride, h->n_x);
+    if (((uintptr_t)d_x & 15) || (x_stride & 1) || (want_grad && (((uintptr_t)d_grad & 15) || (grad_stride & 1))))
+        return h->fail(VGPA_EINVAL, "device buffers must be 16-byte aligned with even strides");
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * h->d.B, st), "cudaMemsetAsync(status)");
+    Extra ex{};
+    for (int p0 = 0; p0 < h->d.B; p0 += h->chunk) {
+        const int count = std::min(h->chunk, h->d.B - p0);
+        run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, st);
+    }
+    CK(cudaGetLastError(), "kernel launch");
+    h->last_stream = st;
+    h->status_dirty = true;
+    return VGPA_OK;
+}
+
+int vgpa_sync(vgpa_handle* h)
+{
+    if (!h) return VGPA_EINVAL;
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(h->last_stream), "cudaStreamSynchronize");
+    return check_status(h);
+}
+
+int vgpa_eval(vgpa_handle* h, const double* x, int64_t x_stride, int want_grad, double* F, double* grad,
+              int64_t grad_stride)
+{
+    if (!h) return VGPA_EINVAL;
+    if (x == nullptr || F == nullptr) return h->fail(VGPA_EINVAL, "x / F is NULL");
+    if (want_grad && grad == nullptr) return h->fail(VGPA_EINVAL, "want_grad set but grad is NULL");
+    if (x_stride != 0 && x_stride < h->n_x) return h->fail(VGPA_EINVAL, "x_stride %lld < %lld", (long long)x_stride, h->n_x);
+    if (want_grad && h->d.B > 1 && grad_stride < h->n_x)
+        return h->fail(VGPA_EINVAL, "grad_stride %lld < %lld", (long long)grad_stride, h->n_x);
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    const int B = h->d.B, C = h->chunk;
+    const long long nx = h->n_x;
+    const bool shared_x = (x_stride == 0);
+    // staging (lazily sized): per slot one chunk of x rows and gradient rows
+    const size_t xbytes = sizeof(double) * (size_t)nx * (shared_x ? 1 : C);
+    const int nslots = (B > C) ? 2 : 1;
+    for (int q = 0; q < nslots; ++q) {
+        if (h->st_x[q].bytes < xbytes) CK(h->st_x[q].alloc(xbytes), "cudaMalloc(x staging)");
+        if (want_grad && h->st_g[q].bytes < sizeof(double) * (size_t)nx * C)
+            CK(h->st_g[q].alloc(sizeof(double) * (size_t)nx * C), "cudaMalloc(grad staging)");
+    }
+    if (h->st_F.bytes < sizeof(double) * B) CK(h->st_F.alloc(sizeof(double) * B), "cudaMalloc(F)");
+    CK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * B, h->s_comp), "cudaMemsetAsync(status)");
+    Extra ex{};
+    int ci = 0;
+    for (int p0 = 0; p0 < B; p0 += C, ++ci) {
+        const int count = std::min(C, B - p0);
+        const int q = ci & 1;
+        // slot q: its previous gradients must have left and its previous x must be consumed
+        if (ci >= 2) {
+            CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[q], 0), "cudaStreamWaitEvent");
+            CK(cudaStreamWaitEvent(h->s_comp, h->ev_d2h[q], 0), "cudaStreamWaitEvent");
+        }
+        if (!shared_x || ci == 0) {
+            if (shared_x) {
+                CK(cudaMemcpyAsync(h->st_x[0].p, x, sizeof(double) * nx, cudaMemcpyHostToDevice, h->s_h2d), "H2D x");
+            } else if (x_stride == nx) {
+                CK(cudaMemcpyAsync(h->st_x[q].p, x + (long long)p0 * x_stride, sizeof(double) * nx * count,
+                                   cudaMemcpyHostToDevice, h->s_h2d), "H2D x");
+            } else {
+                CK(cudaMemcpy2DAsync(h->st_x[q].p, sizeof(double) * nx, x + (long long)p0 * x_stride,
+                                     sizeof(double) * x_stride, sizeof(double) * nx, count,
+                                     cudaMemcpyHostToDevice, h->s_h2d), "H2D x");
+            }
+        }
+        CK(cudaEventRecord(h->ev_h2d[q], h->s_h2d), "cudaEventRecord");
+        CK(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[q], 0), "cudaStreamWaitEvent");
+        // kernels index problems globally (p0 + lp): offset the staged pointers accordingly
+        const double* dx = shared_x ? h->st_x[0].as<double>() : h->st_x[q].as<double>() - (long long)p0 * nx;
+        double* dg = want_grad ? h->st_g[q].as<double>() - (long long)p0 * nx : nullptr;
+        run_chunk(h, dx, shared_x ? 0 : nx, want_grad, h->st_F.as<double>(), dg, nx, p0, count, ex, h->s_comp);
+        CK(cudaGetLastError(), "kernel launch");
+        CK(cudaEventRecord(h->ev_comp[q], h->s_comp), "cudaEventRecord");
+        if (want_grad) {
+            CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[q], 0), "cudaStreamWaitEvent");
+            if (grad_stride == nx || count == 1) {
+                CK(cudaMemcpyAsync(grad + (long long)p0 * grad_stride, h->st_g[q].p, sizeof(double) * nx * count,
+                                   cudaMemcpyDeviceToHost, h->s_d2h), "D2H grad");
+            } else {
+                CK(cudaMemcpy2DAsync(grad + (long long)p0 * grad_stride, sizeof(double) * grad_stride, h->st_g[q].p,
+                                     sizeof(double) * nx, sizeof(double) * nx, count, cudaMemcpyDeviceToHost,
+                                     h->s_d2h), "D2H grad");
+            }
+            CK(cudaEventRecord(h->ev_d2h[q], h->s_d2h), "cudaEventRecord");
+        }
+    }
+    CK(cudaMemcpyAsync(F, h->st_F.p, sizeof(double) * B, cudaMemcpyDeviceToHost, h->s_comp), "D2H F");
+    CK(cudaStreamSynchronize(h->s_comp), "cudaStreamSynchronize");
+    CK(cudaStreamSynchronize(h->s_d2h), "cudaStreamSynchronize");
+    h->status_dirty = true;
+    return check_status(h);
+}
+
+int vgpa_eval_full(vgpa_handle* h, int64_t problem, const double* x, const vgpa_full_out* out)
+{
+    if (!h) return VGPA_EINVAL;
+    if (x == nullptr || out == nullptr) return h->fail(VGPA_EINVAL, "x / out is NULL");
+    if (problem < 0 || problem >= h->d.B) return h->fail(VGPA_EINVAL, "problem index %lld out of range", (long long)problem);
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    const long long nx = h->n_x, N = h->d.N, D = h->d.D, nv = N * D, nm = N * D * D;
+    DevBuf dx, dg, dF, dl, dp, def, dedf, dparts;
+    auto cleanup = [&]() { for (DevBuf* b : {&dx, &dg, &dF, &dl, &dp, &def, &dedf, &dparts}) b->release(); };
+    cudaError_t e;
+    if ((e = dx.alloc(sizeof(double) * nx)) != cudaSuccess || (e = dg.alloc(sizeof(double) * nx)) != cudaSuccess ||
+        (e = dF.alloc(sizeof(double) * h->d.B)) != cudaSuccess || (e = dl.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dp.alloc(sizeof(double) * nm)) != cudaSuccess || (e = def.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dedf.alloc(sizeof(double) * nm)) != cudaSuccess || (e = dparts.alloc(sizeof(double) * 3)) != cudaSuccess ||
+        (e = cudaMemcpy(dx.p, x, sizeof(double) * nx, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return h->cuda_fail(e, "vgpa_eval_full setup");
+    }
+    Extra ex{};
+    ex.lamt = dl.as<double>(); ex.psit = dp.as<double>(); ex.Efx = def.as<double>(); ex.Edf = dedf.as<double>();
+    ex.parts = dparts.as<double>();
+    cudaMemsetAsync(h->status.p, 0, sizeof(int) * h->d.B, h->s_comp);
+    // kernels address x / grad / F by global problem index
+    run_chunk(h, dx.as<double>() - problem * nx, nx, 1, dF.as<double>(), dg.as<double>() - problem * nx, nx,
+              (int)problem, 1, ex, h->s_comp);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_comp);
+    if (e != cudaSuccess) {
+        cleanup();
+        return h->cuda_fail(e, "vgpa_eval_full kernels");
+    }
+    auto back = [&](double* dst, const void* src, long long n) {
+        if (dst && e == cudaSuccess) e = cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    };
+    back(out->F, dF.as<double>() + problem, 1);
+    back(out->parts, dparts.p, 3);
+    back(out->grad, dg.p, nx);
+    back(out->mt, h->scratch.mt, nv);
+    back(out->st, h->scratch.st, nm);
+    back(out->lamt, dl.p, nv);
+    back(out->psit, dp.p, nm);
+    back(out->Efx, def.p, nv);
+    back(out->Edf, dedf.p, nm);
+    back(out->dEsde_dm, h->scratch.dEm, nv);
+    back(out->dEsde_ds, h->scratch.dEs, nm);
+    cleanup();
+    if (e != cudaSuccess) return h->cuda_fail(e, "vgpa_eval_full copy-back");
+    h->status_dirty = true;
+    return check_status(h);
+}
+
+// ---- stand-alone sweeps (FwdOde.__call__ / BwdOde.__call__) -------------------------
+static int check_sweep_args(int method, int D, int N, double dt)
+{
+    if (method < 0 || method > 3) { g_create_error = "Integration method is unknown"; return VGPA_EINVAL; }
+    if (D != 1 && D != 3 && D != 40) { g_create_error = "unsupported state dimension (1, 3 or 40)"; return VGPA_EINVAL; }
+    if (N < 2) { g_create_error = "need at least two time points"; return VGPA_EINVAL; }
+    if (!(dt > 0.0)) { g_create_error = "Discrete time step should be strictly positive"; return VGPA_EINVAL; }
+    return VGPA_OK;
+}
+
+int vgpa_solve_fwd(int device, int method, int D, int N, double dt, const double* A, const double* b,
+                   const double* m0, const double* s0, const double* sigma, double* mt, double* st)
+{
+    int rc = check_sweep_args(method, D, N, dt);
+    if (rc) return rc;
+    if (!A || !b || !m0 || !s0 || !sigma || !mt || !st) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const long long nv = (long long)N * D, nm = (long long)N * D * D;
+    DevBuf dx, dm0, ds0, dsig, dmt, dst;
+    cudaError_t e;
+    auto cleanup = [&]() { for (DevBuf* q : {&dx, &dm0, &ds0, &dsig, &dmt, &dst}) q->release(); };
+    if ((e = dx.alloc(sizeof(double) * (nm + nv))) != cudaSuccess || (e = dm0.alloc(sizeof(double) * D)) != cudaSuccess ||
+        (e = ds0.alloc(sizeof(double) * D * D)) != cudaSuccess || (e = dsig.alloc(sizeof(double) * D)) != cudaSuccess ||
+        (e = dmt.alloc(sizeof(double) * nv)) != cudaSuccess || (e = dst.alloc(sizeof(double) * nm)) != cudaSuccess ||
+        (e = cudaMemcpy(dx.p, A, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dx.as<double>() + nm, b, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dm0.p, m0, sizeof(double) * D, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(ds0.p, s0, sizeof(double) * D * D, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dsig.p, sigma, sizeof(double) * D, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_solve_fwd: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    Batch bt{};
+    bt.model = (D == 40) ? MODEL_L96 : (D == 3 ? MODEL_L63 : MODEL_OU);
+    bt.method = method; bt.D = D; bt.N = N; bt.B = 1; bt.dt = dt; bt.dt_model = dt;
+    bt.sigma = dsig.as<double>(); bt.m0 = dm0.as<double>(); bt.s0 = ds0.as<double>();
+    Scratch sc{};
+    sc.mt = dmt.as<double>(); sc.st = dst.as<double>();
+    if (D == 40) launch_l96_fwd(bt, sc, dx.as<double>(), 0, 0, 1, nullptr);
+    else launch_small_fwd(bt, sc, dx.as<double>(), 0, 0, 1, nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mt, dmt.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(st, dst.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA error in vgpa_solve_fwd: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    return VGPA_OK;
+}
+
+int vgpa_solve_bwd(int device, int method, int D, int N, double dt, const double* A, const double* dEm,
+                   const double* dEs, const double* jm, const double* js, double* lam, double* psi)
+{
+    int rc = check_sweep_args(method, D, N, dt);
+    if (rc) return rc;
+    if (!A || !dEm || !dEs || !jm || !js || !lam || !psi) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const long long nv = (long long)N * D, nm = (long long)N * D * D;
+    DevBuf dA, dgm, dgs, djm, djs, dl, dp;
+    cudaError_t e;
+    auto cleanup = [&]() { for (DevBuf* q : {&dA, &dgm, &dgs, &djm, &djs, &dl, &dp}) q->release(); };
+    if ((e = dA.alloc(sizeof(double) * nm)) != cudaSuccess || (e = dgm.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dgs.alloc(sizeof(double) * nm)) != cudaSuccess || (e = djm.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = djs.alloc(sizeof(double) * nm)) != cudaSuccess || (e = dl.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dp.alloc(sizeof(double) * nm)) != cudaSuccess ||
+        (e = cudaMemcpy(dA.p, A, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dgm.p, dEm, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dgs.p, dEs, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(djm.p, jm, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(djs.p, js, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_solve_bwd: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    launch_bwd_dense(method, D, N, dt, dA.as<double>(), dgm.as<double>(), dgs.as<double>(), djm.as<double>(),
+                     djs.as<double>(), dl.as<double>(), dp.as<double>(), nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(lam, dl.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(psi, dp.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA error in vgpa_solve_bwd: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    return VGPA_OK;
+}
+
+int vgpa_model_energy(int device, int model, int D, int N, double dt_model, const double* theta,
+                      const double* sigma, const double* A, const double* b, const double* m, const double* S,
+                      double* Esde, double* Ef, double* Edf, double* dEm, double* dEs)
+{
+    if (model < 0 || model > 3) { g_create_error = "Unknown stochastic model"; return VGPA_EINVAL; }
+    const int needD = (model == VGPA_MODEL_L63) ? 3 : (model == VGPA_MODEL_L96 ? 40 : 1);
+    if (D != needD || N < 2 || !(dt_model > 0.0)) { g_create_error = "Wrong dimensions for model.energy"; return VGPA_EINVAL; }
+    if (!theta || !sigma || !A || !b || !m || !S || !Esde || !Ef || !Edf || !dEm || !dEs) {
+        g_create_error = "NULL argument";
+        return VGPA_EINVAL;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const long long nv = (long long)N * D, nm = (long long)N * D * D;
+    const int nth = n_theta(model);
+    DevBuf dx, dth, dsig, dmt, dst, dgm, dgs, des, def, dedf, dparts, dzero, dF, dstat;
+    auto cleanup = [&]() {
+        for (DevBuf* q : {&dx, &dth, &dsig, &dmt, &dst, &dgm, &dgs, &des, &def, &dedf, &dparts, &dzero, &dF, &dstat})
+            q->release();
+    };
+    cudaError_t e;
+    if ((e = dx.alloc(sizeof(double) * (nm + nv))) != cudaSuccess || (e = dth.alloc(sizeof(double) * nth)) != cudaSuccess ||
+        (e = dsig.alloc(sizeof(double) * D)) != cudaSuccess || (e = dmt.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dst.alloc(sizeof(double) * nm)) != cudaSuccess || (e = dgm.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dgs.alloc(sizeof(double) * nm)) != cudaSuccess || (e = des.alloc(sizeof(double) * N)) != cudaSuccess ||
+        (e = def.alloc(sizeof(double) * nv)) != cudaSuccess || (e = dedf.alloc(sizeof(double) * nm)) != cudaSuccess ||
+        (e = dparts.alloc(sizeof(double) * 3)) != cudaSuccess || (e = dzero.alloc(sizeof(double))) != cudaSuccess ||
+        (e = dF.alloc(sizeof(double))) != cudaSuccess || (e = dstat.alloc(sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(dzero.p, 0, sizeof(double))) != cudaSuccess || (e = cudaMemset(dstat.p, 0, sizeof(int))) != cudaSuccess ||
+        (e = cudaMemcpy(dx.p, A, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dx.as<double>() + nm, b, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dth.p, theta, sizeof(double) * nth, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dsig.p, sigma, sizeof(double) * D, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dmt.p, m, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dst.p, S, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_model_energy: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    Batch bt{};
+    bt.model = model; bt.method = ODE_EULER; bt.D = D; bt.N = N; bt.M = 0; bt.B = 1;
+    bt.dt = dt_model; bt.dt_model = dt_model;
+    bt.theta = dth.as<double>(); bt.sigma = dsig.as<double>(); bt.R = dsig.as<double>();
+    bt.E0 = dzero.as<double>();
+    Scratch sc{};
+    sc.mt = dmt.as<double>(); sc.st = dst.as<double>(); sc.dEm = dgm.as<double>(); sc.dEs = dgs.as<double>();
+    sc.esde_t = des.as<double>(); sc.status = dstat.as<int>();
+    Extra ex{};
+    ex.Efx = def.as<double>(); ex.Edf = dedf.as<double>(); ex.parts = dparts.as<double>();
+    if (model == VGPA_MODEL_L96) launch_l96_energy(bt, sc, dx.as<double>(), 0, 0, 1, ex, nullptr);
+    else launch_small_energy(bt, sc, dx.as<double>(), 0, 0, 1, ex, nullptr);
+    launch_finalize(bt, sc, dF.as<double>(), 0, 1, ex, nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    double parts[3] = {0, 0, 0};
+    int stat = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(parts, dparts.p, sizeof parts, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&stat, dstat.p, sizeof stat, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(Ef, def.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(Edf, dedf.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dEm, dgm.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dEs, dgs.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA error in vgpa_model_energy: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    if (stat != 0) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "Matrix is not positive definite: S(t) at time index %d", stat - 1);
+        g_create_error = buf;
+        return VGPA_ENOTPD;
+    }
+    *Esde = parts[1];
+    return VGPA_OK;
+}
+
+void* vgpa_host_alloc(int64_t bytes)
+{
+    void* p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void vgpa_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int64_t vgpa_launch_count(const vgpa_handle* h) { return h ? h->launches : 0; }
+int64_t vgpa_chunk_size(const vgpa_handle* h) { return h ? h->chunk : 0; }
+int64_t vgpa_scratch_in_use(const vgpa_handle* h)
+{
+    if (!h) return 0;
+    return (int64_t)(h->sc_mt.bytes + h->sc_st.bytes + h->sc_dEm.bytes + h->sc_dEs.bytes + h->sc_esde.bytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// common.cuh -- shared declarations of the sm_100a VGPA kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vgpa {
+
+enum Model { MODEL_DW = 0, MODEL_OU = 1, MODEL_L63 = 2, MODEL_L96 = 3 };
+enum Method { ODE_EULER = 0, ODE_HEUN = 1, ODE_RK2 = 2, ODE_RK4 = 3 };
+
+// Device-resident description of a problem batch (all pointers are device
+// pointers; *_stride in elements, 0 = shared by every problem).
+struct Batch {
+    int model, method, D, N, M, B;
+    double dt, dt_model;
+    const double* theta;  long long theta_stride;
+    const double* sigma;  long long sigma_stride;
+    const double* R;      long long R_stride;
+    const long long* obs_t;   // M
+    const int* obs_index;     // N : ordinal of the observation at grid index t, or -1
+    const double* obs_y;  long long obs_y_stride;
+    const double* m0;     long long m0_stride;
+    const double* s0;     long long s0_stride;
+    const double* E0;     long long E0_stride;
+};
+
+// Per-pass (chunk) scratch: trajectories of the marginal moments, the SDE-energy
+// gradients and the per-time-step energy.  Problem-major: [p][t][...].
+struct Scratch {
+    double* mt;      // (C, N, D)
+    double* st;      // (C, N, D, D)
+    double* dEm;     // (C, N, D)
+    double* dEs;     // (C, N, D, D)
+    double* esde_t;  // (C, N)
+    int* status;     // (C) : 0 ok, else 1 + time index of the first non-PD S(t)
+};
+
+// Optional per-problem trajectory outputs (vgpa_eval_full); null = not stored.
+struct Extra {
+    double* lamt;  // (N, D)
+    double* psit;  // (N, D, D)
+    double* Efx;   // (N, D)
+    double* Edf;   // (N, D, D)
+    double* parts; // (3) E0, Esde, Eobs
+};
+
+// ---- launchers (one translation unit each) --------------------------------
+// p0: first problem of the chunk; count: problems in the chunk.
+void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                      int p0, int count, cudaStream_t st);
+void launch_small_energy(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                         int p0, int count, const Extra& ex, cudaStream_t st);
+void launch_small_bwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                      double* grad, long long grad_stride, int p0, int count, const Extra& ex,
+                      cudaStream_t st);
+
+void launch_l96_fwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                    int p0, int count, cudaStream_t st);
+void launch_l96_energy(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                       int p0, int count, const Extra& ex, cudaStream_t st);
+void launch_l96_bwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
+                    double* grad, long long grad_stride, int p0, int count, const Extra& ex,
+                    cudaStream_t st);
+
+// F[p] = E0 + trapz(esde_t) (/sigma for DW, OU) + Eobs.
+void launch_finalize(const Batch& b, const Scratch& s, double* F, int p0, int count,
+                     const Extra& ex, cudaStream_t st);
+
+// Stand-alone backward sweep with dense jump tables (BwdOde.__call__).
+void launch_bwd_dense(int method, int D, int N, double dt, const double* A, const double* dEm,
+                      const double* dEs, const double* jm, const double* js, double* lam,
+                      double* psi, cudaStream_t st);
+
+}  // namespace vgpa

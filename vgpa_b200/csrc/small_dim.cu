@@ -1,0 +1,732 @@
+// small_dim.cu -- D = 1 (Double Well, Ornstein-Uhlenbeck) and D = 3 (Lorenz 63)
+// kernels.  With a state this small one inference problem fits in the registers
+// of ONE thread, so the sequential sweeps run one thread per problem (a batch
+// of B problems is B independent register-resident recurrences) and the
+// time-parallel stage runs one thread per (problem, time index).
+//
+// Reference behaviour reproduced (paths relative to the reference root):
+//   forward sweep   src/numerics/{euler,heun,runge_kutta2,runge_kutta4}.py solve_fwd
+//   backward sweep  same files, solve_bwd; RHS in src/numerics/ode_solver.py:31-95
+//   energies        src/dynamics/double_well.py:169-260, ornstein_uhlenbeck.py:165-232,
+//                   lorenz_63.py:237-568
+//   jumps           src/var_bayes/gaussian_like.py:155-243
+//   gradient        src/var_bayes/variational.py:202-334
+//   F               variational.py:199, utilities.py:144-201, gaussian_like.py:69-153
+#include "common.cuh"
+
+namespace vgpa {
+
+// ---------------------------------------------------------------------------
+// register-resident D x D helpers
+// ---------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void ld_vec(const double* __restrict__ g, double* r)
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) r[i] = __ldg(g + i);
+}
+
+// ode_solver.py:44   -A m + b
+template <int D>
+__device__ __forceinline__ void fun_m(const double* m, const double* A, const double* b, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += A[i * D + k] * m[k];
+        o[i] = -s + b[i];
+    }
+}
+// ode_solver.py:60   -A S - S A^T + Sigma   (Sigma diagonal)
+template <int D>
+__device__ __forceinline__ void fun_S(const double* S, const double* A, const double* sig, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double p = 0.0, q = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                p += A[i * D + k] * S[k * D + j];
+                q += S[i * D + k] * A[j * D + k];
+            }
+            o[i * D + j] = -p - q + (i == j ? sig[i] : 0.0);
+        }
+}
+// ode_solver.py:77   -g + A lam
+template <int D>
+__device__ __forceinline__ void fun_lam(const double* g, const double* A, const double* lam, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += A[i * D + k] * lam[k];
+        o[i] = -g[i] + s;
+    }
+}
+// ode_solver.py:94   -G + Psi A + A^T Psi
+template <int D>
+__device__ __forceinline__ void fun_psi(const double* G, const double* A, const double* P, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double p = 0.0, q = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                p += P[i * D + k] * A[k * D + j];
+                q += A[k * D + i] * P[k * D + j];
+            }
+            o[i * D + j] = -G[i * D + j] + p + q;
+        }
+}
+template <int n>
+__device__ __forceinline__ void axpy(const double* y, double a, const double* x, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < n; ++i) o[i] = y[i] + a * x[i];
+}
+template <int n>
+__device__ __forceinline__ void mid(const double* p, const double* q, double* o)
+{
+#pragma unroll
+    for (int i = 0; i < n; ++i) o[i] = 0.5 * (p[i] + q[i]);
+}
+
+// ---------------------------------------------------------------------------
+// forward sweep: one thread per problem
+// ---------------------------------------------------------------------------
+template <int D, int METHOD>
+__global__ void __launch_bounds__(64)
+small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count)
+{
+    constexpr int DD = D * D;
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= count) return;
+    const int p = p0 + lp, N = b.N;
+    const double* A = x + (long long)p * xs;
+    const double* bo = A + (long long)N * DD;
+    double sig[D], m[D], S[DD];
+    ld_vec<D>(b.sigma + p * b.sigma_stride, sig);
+    ld_vec<D>(b.m0 + p * b.m0_stride, m);
+    ld_vec<DD>(b.s0 + p * b.s0_stride, S);
+    double* mt = s.mt + (long long)lp * N * D;
+    double* st = s.st + (long long)lp * N * DD;
+#pragma unroll
+    for (int i = 0; i < D; ++i) mt[i] = m[i];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) st[i] = S[i];
+    const double dt = b.dt, h = 0.5 * dt;
+    double Ak[DD], bk[D], An[DD], bn[D];
+    ld_vec<DD>(A, Ak);
+    ld_vec<D>(bo, bk);
+    for (int k = 0; k < N - 1; ++k) {
+        ld_vec<DD>(A + (long long)(k + 1) * DD, An);
+        ld_vec<D>(bo + (long long)(k + 1) * D, bn);
+        double mn[D], Sn[DD];
+        if (METHOD == ODE_EULER) {  // euler.py:84-87
+            double v1[D], k1[DD];
+            fun_m<D>(m, Ak, bk, v1);
+            axpy<D>(m, dt, v1, mn);
+            fun_S<D>(S, Ak, sig, k1);
+            axpy<DD>(S, dt, k1, Sn);
+        } else if (METHOD == ODE_HEUN) {  // heun.py:91-106
+            double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+            fun_m<D>(m, Ak, bk, v1);
+            axpy<D>(m, dt, v1, vt);
+            fun_m<D>(vt, An, bn, v2);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mn[i] = m[i] + h * (v1[i] + v2[i]);
+            fun_S<D>(S, Ak, sig, k1);
+            axpy<DD>(S, dt, k1, tmp);
+            fun_S<D>(tmp, An, sig, k2);
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Sn[i] = S[i] + h * (k1[i] + k2[i]);
+        } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:92,96 (inner stage: S in place of A)
+            double am[DD], bm[D], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+            mid<DD>(Ak, An, am);
+            mid<D>(bk, bn, bm);
+            fun_m<D>(m, Ak, bk, v1);
+            axpy<D>(m, h, v1, vt);
+            fun_m<D>(vt, am, bm, v2);
+            axpy<D>(m, dt, v2, mn);
+            fun_S<D>(S, S, sig, k1);
+            axpy<DD>(S, h, k1, tmp);
+            fun_S<D>(tmp, am, sig, k2);
+            axpy<DD>(S, dt, k2, Sn);
+        } else {  // runge_kutta4.py:93-108
+            double am[DD], bm[D], v1[D], v2[D], v3[D], v4[D], vt[D];
+            double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
+            mid<DD>(Ak, An, am);
+            mid<D>(bk, bn, bm);
+            fun_m<D>(m, Ak, bk, v1);
+            axpy<D>(m, h, v1, vt);
+            fun_m<D>(vt, am, bm, v2);
+            axpy<D>(m, h, v2, vt);
+            fun_m<D>(vt, am, bm, v3);
+            axpy<D>(m, dt, v3, vt);
+            fun_m<D>(vt, An, bn, v4);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                mn[i] = m[i] + dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0;
+            fun_S<D>(S, Ak, sig, k1);
+            axpy<DD>(S, h, k1, tmp);
+            fun_S<D>(tmp, am, sig, k2);
+            axpy<DD>(S, h, k2, tmp);
+            fun_S<D>(tmp, am, sig, k3);
+            axpy<DD>(S, dt, k3, tmp);
+            fun_S<D>(tmp, An, sig, k4);
+#pragma unroll
+            for (int i = 0; i < DD; ++i)
+                Sn[i] = S[i] + dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            m[i] = mn[i];
+            bk[i] = bn[i];
+            mt[(long long)(k + 1) * D + i] = mn[i];
+        }
+#pragma unroll
+        for (int i = 0; i < DD; ++i) {
+            S[i] = Sn[i];
+            Ak[i] = An[i];
+            st[(long long)(k + 1) * DD + i] = Sn[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-time-step SDE energy, its m/S gradients, and <f>, <df/dx>
+// ---------------------------------------------------------------------------
+struct Moments1 {  // gaussian_moments.py:57-74,108-122,155-167
+    double E2, E3, E4, E6, Dm2, Dm3, Dm4, Dm6, Ds3, Ds4, Ds6;
+    __device__ __forceinline__ Moments1(double m, double v)
+    {
+        const double m2 = m * m, m3 = m2 * m, m4 = m2 * m2, m5 = m4 * m, m6 = m3 * m3;
+        const double v2 = v * v, v3 = v2 * v;
+        E2 = m2 + v;
+        E3 = m3 + 3 * m * v;
+        E4 = m4 + 6 * m2 * v + 3 * v2;
+        E6 = m6 + 15 * m4 * v + 45 * m2 * v2 + 15 * v3;
+        Dm2 = 2 * m;
+        Dm3 = 3 * (m2 + v);
+        Dm4 = 4 * (m3 + 3 * m * v);
+        Dm6 = 6 * (m5 + 10 * m3 * v + 15 * m * v2);
+        Ds3 = 3 * m;
+        Ds4 = 6 * (m2 + v);
+        Ds6 = 15 * m4 + 90 * m2 * v + 45 * v2;
+    }
+};
+
+// <f> and <df/dx> at one time index (needed by the energy output and again by
+// the gradient assembly, which recomputes them instead of storing them).
+template <int MODEL, int D>
+__device__ __forceinline__ void drift_moments(const double* th, const double* m, const double* S,
+                                              double* Ef, double* Edf)
+{
+    if (MODEL == MODEL_DW) {  // double_well.py:220,223
+        const double E2 = m[0] * m[0] + S[0], E3 = m[0] * m[0] * m[0] + 3 * m[0] * S[0];
+        Ef[0] = 4.0 * (th[0] * m[0] - E3);
+        Edf[0] = 4.0 * (th[0] - 3.0 * E2);
+    } else if (MODEL == MODEL_OU) {  // ornstein_uhlenbeck.py:211,214
+        Ef[0] = -th[0] * m[0];
+        Edf[0] = -th[0];
+    } else {  // lorenz_63.py:319-326 (reads S[2,0] and S[1,0])
+        const double vS = th[0], vR = th[1], vB = th[2];
+        Ef[0] = vS * (m[1] - m[0]);
+        Ef[1] = vR * m[0] - m[1] - S[2 * D + 0] - m[0] * m[2];
+        Ef[2] = S[1 * D + 0] + m[0] * m[1] - vB * m[2];
+        Edf[0] = -vS;        Edf[1] = vS;   Edf[2] = 0.0;
+        Edf[3] = vR - m[2];  Edf[4] = -1.0; Edf[5] = -m[0];
+        Edf[6] = m[1];       Edf[7] = m[0]; Edf[8] = -vB;
+    }
+}
+
+// Lorenz 63: each residual r_i(x) = f_i(x) + (A x)_i - b_i is a quadratic
+// polynomial  c + l.x + s x_a x_b  of the Gaussian state x ~ N(m, S), so with
+// u = l + s (m_b e_a + m_a e_b),  mu = <r> = c + l.m + s (m_a m_b + S_ab):
+//   <r^2>        = mu^2 + u'Su + s^2 (S_aa S_bb + S_ab^2)
+//   d<r^2>/dm    = 2 mu u + 2 s ((Su)_b e_a + (Su)_a e_b)
+//   d<r^2>/dS    = u u' + mu s (E_ab + E_ba) + s^2 (S_bb E_aa + S_aa E_bb + S_ab (E_ab + E_ba))
+// This equals the reference's hand-expanded moment expressions
+// (lorenz_63.py:393-566) EXCEPT that the reference differentiates w.r.t. each
+// off-diagonal S_xy as ONE variable, i.e. its off-diagonal entries are twice the
+// symmetric per-entry gradient; that factor is applied at the end (:564-566).
+__device__ __forceinline__ void l63_energy(const double* th, const double* iS, const double* A,
+                                           const double* bt, const double* m, const double* S,
+                                           double& esde, double* dEm, double* dEs)
+{
+    const double vS = th[0], vR = th[1], vB = th[2];
+    // the reference reads the UPPER triangle of S (lorenz_63.py:388-390)
+    const double U[9] = {S[0], S[1], S[2], S[1], S[4], S[5], S[2], S[5], S[8]};
+    const double l[9] = {A[0] - vS, A[1] + vS, A[2], A[3] + vR, A[4] - 1.0, A[5],
+                         A[6], A[7], A[8] - vB};
+    const double sg[3] = {0.0, -1.0, 1.0};
+    const int ia[3] = {0, 0, 0}, ib[3] = {0, 2, 1};
+    esde = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dEm[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dEs[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double s = sg[i];
+        const int a = ia[i], c = ib[i];
+        double u[3] = {l[i * 3 + 0], l[i * 3 + 1], l[i * 3 + 2]};
+        double mu = -bt[i] + u[0] * m[0] + u[1] * m[1] + u[2] * m[2];
+        double extra = 0.0;
+        if (i > 0) {
+            mu += s * (m[a] * m[c] + U[a * 3 + c]);
+            u[a] += s * m[c];
+            u[c] += s * m[a];
+            extra = U[a * 3 + a] * U[c * 3 + c] + U[a * 3 + c] * U[a * 3 + c];
+        }
+        double Su[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Su[r] = U[r * 3 + 0] * u[0] + U[r * 3 + 1] * u[1] + U[r * 3 + 2] * u[2];
+        const double Er2 = mu * mu + (u[0] * Su[0] + u[1] * Su[1] + u[2] * Su[2]) + extra;
+        const double w = 0.5 * iS[i];
+        esde += w * Er2;
+        double gm[3] = {2 * mu * u[0], 2 * mu * u[1], 2 * mu * u[2]};
+        double G[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) G[r * 3 + q] = u[r] * u[q];
+        if (i > 0) {
+            gm[a] += 2 * s * Su[c];
+            gm[c] += 2 * s * Su[a];
+            const double off = mu * s + U[a * 3 + c];
+            G[a * 3 + c] += off;
+            G[c * 3 + a] += off;
+            G[a * 3 + a] += U[c * 3 + c];
+            G[c * 3 + c] += U[a * 3 + a];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dEm[r] += w * gm[r];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) dEs[r] += w * G[r];
+    }
+    // off-diagonal convention of the reference (see above)
+    dEs[1] *= 2.0; dEs[2] *= 2.0; dEs[3] *= 2.0; dEs[5] *= 2.0; dEs[6] *= 2.0; dEs[7] *= 2.0;
+}
+
+template <int MODEL, int D>
+__global__ void __launch_bounds__(128)
+small_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count,
+                    Extra ex)
+{
+    constexpr int DD = D * D;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = b.N;
+    if (idx >= (long long)count * N) return;
+    const int lp = (int)(idx / N), t = (int)(idx % N), p = p0 + lp;
+    const double* A = x + (long long)p * xs + (long long)t * DD;
+    const double* bo = x + (long long)p * xs + (long long)N * DD + (long long)t * D;
+    const double* th = b.theta + p * b.theta_stride;
+    const double* sg = b.sigma + p * b.sigma_stride;
+    double At[DD], bt[D], m[D], S[DD];
+    ld_vec<DD>(A, At);
+    ld_vec<D>(bo, bt);
+    const long long oV = ((long long)lp * N + t) * D, oM = ((long long)lp * N + t) * DD;
+#pragma unroll
+    for (int i = 0; i < D; ++i) m[i] = s.mt[oV + i];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) S[i] = s.st[oM + i];
+    double e, dm[D], dS[DD];
+    if (MODEL == MODEL_DW) {  // double_well.py:214,243,248 (8*E6 in the energy, 16*Dm6 in the gradient)
+        const Moments1 g(m[0], S[0]);
+        const double c = 4.0 * th[0] + At[0], c2 = c * c, bb = bt[0];
+        e = 8.0 * (g.E6 - c * g.E4 + bb * g.E3) + (c2 * g.E2) - (2.0 * bb * c * m[0]) + bb * bb;
+        dm[0] = 0.5 * (16.0 * g.Dm6 - 8.0 * c * g.Dm4 + 8.0 * bb * g.Dm3 + c2 * g.Dm2 - 2.0 * bb * c) / sg[0];
+        dS[0] = 0.5 * (16.0 * g.Ds6 - 8.0 * c * g.Ds4 + 8.0 * bb * g.Ds3 + c2 * 1.0) / sg[0];
+    } else if (MODEL == MODEL_OU) {  // ornstein_uhlenbeck.py:205,217,221
+        const double E2 = m[0] * m[0] + S[0], d = th[0] - At[0], q1 = d * d;
+        e = E2 * q1 + 2.0 * m[0] * d * bt[0] + bt[0] * bt[0];
+        dm[0] = (m[0] * q1 + th[0] * bt[0] - At[0] * bt[0]) / sg[0];
+        dS[0] = 0.5 * q1 / sg[0];
+    } else {
+        double iS[3] = {1.0 / sg[0], 1.0 / sg[1], 1.0 / sg[2]};
+        l63_energy(th, iS, At, bt, m, S, e, dm, dS);
+    }
+    s.esde_t[(long long)lp * N + t] = e;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s.dEm[oV + i] = dm[i];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) s.dEs[oM + i] = dS[i];
+    if (ex.Efx != nullptr && lp == 0) {
+        double Ef[D], Edf[DD];
+        drift_moments<MODEL, D>(th, m, S, Ef, Edf);
+#pragma unroll
+        for (int i = 0; i < D; ++i) ex.Efx[(long long)t * D + i] = Ef[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) ex.Edf[(long long)t * DD + i] = Edf[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward sweep fused with the gradient assembly: one thread per problem.
+// lam, Psi live in registers; dL/dA, dL/db are written as soon as lam[t],
+// Psi[t] exist, so lam/Psi never go to HBM (unless ex.lamt asks for them).
+// ---------------------------------------------------------------------------
+template <int MODEL, int D>
+__device__ __forceinline__ void grad_at(const double* th, const double* isg, double dtm,
+                                        const double* At, const double* bt, const double* m,
+                                        const double* S, const double* lam, const double* Psi,
+                                        double* gA, double* gb)
+{
+    constexpr int DD = D * D;
+    double Ef[D], Edf[DD], db[D];
+    drift_moments<MODEL, D>(th, m, S, Ef, Edf);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {  // variational.py:324-334
+        double am = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) am += At[i * D + k] * m[k];
+        db[i] = isg[i] * (-Ef[i] - am + bt[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {  // variational.py:312-322, :300-310
+            double p1 = 0.0, p2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                p1 += (isg[i] * (Edf[i * D + k] + At[i * D + k])) * S[k * D + j];
+                p2 += Psi[i * D + k] * S[k * D + j];
+            }
+            gA[i * D + j] = dtm * ((p1 - db[i] * m[j]) - lam[i] * m[j] - 2.0 * p2);
+        }
+        gb[i] = dtm * (db[i] + lam[i]);  // variational.py:280,285
+    }
+}
+
+// jm_dense / js_dense: dense jump tables of the stand-alone sweep (BwdOde.__call__,
+// bwd_ode.py:45); null in the batched path, where the jumps come from the observations.
+struct SmallBwdArgs {
+    const double* x; long long xs;
+    double* grad; long long gs;
+    const double* jm_dense; const double* js_dense;
+};
+
+template <int MODEL, int D, int METHOD>
+__global__ void __launch_bounds__(64)
+small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex)
+{
+    constexpr int DD = D * D;
+    const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= count) return;
+    const int p = p0 + lp, N = b.N;
+    const bool dense = a.jm_dense != nullptr;
+    const double* A = a.x + (long long)p * a.xs;
+    const double* bo = A + (long long)N * DD;
+    double* gA = a.grad ? a.grad + (long long)p * a.gs : nullptr;
+    double* gb = a.grad ? gA + (long long)N * DD : nullptr;
+    const double* mt = s.mt + (long long)lp * N * D;
+    const double* st = s.st + (long long)lp * N * DD;
+    const double* dEm = s.dEm + (long long)lp * N * D;
+    const double* dEs = s.dEs + (long long)lp * N * DD;
+    const double* th = dense ? nullptr : b.theta + p * b.theta_stride;
+    const double* oy = dense ? nullptr : b.obs_y + p * b.obs_y_stride;
+    double isg[D], Rv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        isg[i] = dense ? 0.0 : 1.0 / b.sigma[p * b.sigma_stride + i];
+        Rv[i] = dense ? 1.0 : b.R[p * b.R_stride + i];
+    }
+    const bool keep = (ex.lamt != nullptr) && lp == 0;
+    const double dt = b.dt, h = 0.5 * dt, dtm = b.dt_model;
+    double lam[D], Psi[DD];
+#pragma unroll
+    for (int i = 0; i < D; ++i) lam[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < DD; ++i) Psi[i] = 0.0;
+    double At[DD], gt[D], Gt[DD];
+    ld_vec<DD>(A + (long long)(N - 1) * DD, At);
+    ld_vec<D>(dEm + (long long)(N - 1) * D, gt);
+    ld_vec<DD>(dEs + (long long)(N - 1) * DD, Gt);
+    for (int t = N - 1; t >= 0; --t) {
+        double m[D], S[DD], bt[D];
+        if (gA != nullptr) {
+            ld_vec<D>(mt + (long long)t * D, m);
+            ld_vec<DD>(st + (long long)t * DD, S);
+            ld_vec<D>(bo + (long long)t * D, bt);
+        }
+        if (keep) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) ex.lamt[(long long)t * D + i] = lam[i];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) ex.psit[(long long)t * DD + i] = Psi[i];
+        }
+        if (gA != nullptr) {
+            double ga[DD], gbv[D];
+            grad_at<MODEL, D>(th, isg, dtm, At, bt, m, S, lam, Psi, ga, gbv);
+#pragma unroll
+            for (int i = 0; i < DD; ++i) gA[(long long)t * DD + i] = ga[i];
+#pragma unroll
+            for (int i = 0; i < D; ++i) gb[(long long)t * D + i] = gbv[i];
+        }
+        if (t == 0) break;
+        double Am[DD], gm[D], Gm[DD];
+        ld_vec<DD>(A + (long long)(t - 1) * DD, Am);
+        ld_vec<D>(dEm + (long long)(t - 1) * D, gm);
+        ld_vec<DD>(dEs + (long long)(t - 1) * DD, Gm);
+        // jump at index t-1 (gaussian_like.py:188,191 / :235,238); H = I, R diagonal
+        double jm[D], js[D];
+        const int n = dense ? -1 : b.obs_index[t - 1];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            jm[i] = dense ? a.jm_dense[(long long)(t - 1) * D + i] : 0.0;
+            js[i] = 0.0;
+        }
+        if (n >= 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                jm[i] = -(oy[(long long)n * D + i] - mt[(long long)(t - 1) * D + i]) / Rv[i];
+                js[i] = 0.5 / Rv[i];
+            }
+        }
+        double ln[D], Pn[DD];
+        if (METHOD == ODE_EULER) {  // euler.py:146-149
+            double v1[D], k1[DD];
+            fun_lam<D>(gt, At, lam, v1);
+            fun_psi<D>(Gt, At, Psi, k1);
+#pragma unroll
+            for (int i = 0; i < D; ++i) ln[i] = lam[i] - v1[i] * dt + jm[i];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - k1[i] * dt;
+        } else if (METHOD == ODE_HEUN) {  // heun.py:170-185
+            double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+            fun_lam<D>(gt, At, lam, v1);
+            axpy<D>(lam, -dt, v1, vt);
+            fun_lam<D>(gm, Am, vt, v2);
+            fun_psi<D>(Gt, At, Psi, k1);
+            axpy<DD>(Psi, -dt, k1, tmp);
+            fun_psi<D>(Gm, Am, tmp, k2);
+#pragma unroll
+            for (int i = 0; i < D; ++i) ln[i] = lam[i] - h * (v1[i] + v2[i]) + jm[i];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - h * (k1[i] + k2[i]);
+        } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:180-189
+            double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+            mid<DD>(Am, At, am);
+            mid<D>(gm, gt, gmid);
+            mid<DD>(Gm, Gt, Gmid);
+            fun_lam<D>(gt, At, lam, v1);
+            axpy<D>(lam, -h, v1, vt);
+            fun_lam<D>(gmid, am, vt, v2);
+            fun_psi<D>(Gt, At, Psi, k1);
+            axpy<DD>(Psi, -h, k1, tmp);
+            fun_psi<D>(Gmid, am, tmp, k2);
+#pragma unroll
+            for (int i = 0; i < D; ++i) ln[i] = lam[i] - dt * v2[i] + jm[i];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - dt * k2[i];
+        } else {  // runge_kutta4.py:191-206
+            double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], v3[D], v4[D], vt[D];
+            double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
+            mid<DD>(Am, At, am);
+            mid<D>(gm, gt, gmid);
+            mid<DD>(Gm, Gt, Gmid);
+            fun_lam<D>(gt, At, lam, v1);
+            axpy<D>(lam, -h, v1, vt);
+            fun_lam<D>(gmid, am, vt, v2);
+            axpy<D>(lam, -h, v2, vt);
+            fun_lam<D>(gmid, am, vt, v3);
+            axpy<D>(lam, -dt, v3, vt);
+            fun_lam<D>(gm, Am, vt, v4);
+            fun_psi<D>(Gt, At, Psi, k1);
+            axpy<DD>(Psi, -h, k1, tmp);
+            fun_psi<D>(Gmid, am, tmp, k2);
+            axpy<DD>(Psi, -h, k2, tmp);
+            fun_psi<D>(Gmid, am, tmp, k3);
+            axpy<DD>(Psi, -dt, k3, tmp);
+            fun_psi<D>(Gm, Am, tmp, k4);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                ln[i] = lam[i] - dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0 + jm[i];
+#pragma unroll
+            for (int i = 0; i < DD; ++i)
+                Pn[i] = Psi[i] - dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) Pn[i * D + i] += js[i];
+        if (dense) {
+#pragma unroll
+            for (int i = 0; i < DD; ++i) Pn[i] += a.js_dense[(long long)(t - 1) * DD + i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            lam[i] = ln[i];
+            gt[i] = gm[i];
+        }
+#pragma unroll
+        for (int i = 0; i < DD; ++i) {
+            Psi[i] = Pn[i];
+            At[i] = Am[i];
+            Gt[i] = Gm[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// F = E0 + Esde + Eobs : one CTA per problem, fixed-order reductions (bitwise
+// reproducible, so a sharded batch returns the same F as a single-GPU one).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh)
+{
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) sh[tid] += sh[tid + o];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, Extra ex)
+{
+    __shared__ double sh[128];
+    const int lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
+    const int N = b.N, D = b.D, M = b.M, DD = D * D;
+    // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)
+    const double* f = s.esde_t + (long long)lp * N;
+    double acc = 0.0;
+    for (int i = tid; i < N - 1; i += blockDim.x) acc += b.dt_model * (f[i + 1] + f[i]) / 2.0;
+    double Esde = block_sum(acc, sh);
+    if (b.model == MODEL_DW || b.model == MODEL_OU)  // double_well.py:217, ornstein_uhlenbeck.py:208
+        Esde = 0.5 * Esde / b.sigma[p * b.sigma_stride];
+    // observation energy
+    const double* mt = s.mt + (long long)lp * N * D;
+    const double* st = s.st + (long long)lp * N * DD;
+    const double* oy = b.obs_y + p * b.obs_y_stride;
+    const double* R = b.R + p * b.R_stride;
+    double Eobs;
+    const double LOG2PI = 1.8378770664093453;
+    if (D == 1) {  // gaussian_like.py:69-96
+        acc = 0.0;
+        for (int n = tid; n < M; n += blockDim.x) {
+            const long long t = b.obs_t[n];
+            const double y = oy[n], E2 = mt[t] * mt[t] + st[t];
+            acc += (y * y) - 2.0 * y * mt[t] + E2;
+        }
+        const double sm = block_sum(acc, sh);
+        Eobs = 0.5 * sm / R[0] + 0.5 * M * (LOG2PI + log(R[0]));
+    } else {  // gaussian_like.py:98-153; S diagonal indexed by the observation ORDINAL n
+        acc = 0.0;
+        for (int q = tid; q < M * D; q += blockDim.x) {
+            const int n = q / D, i = q % D;
+            const long long t = b.obs_t[n];
+            const double z = (oy[(long long)n * D + i] - mt[t * D + i]) / sqrt(R[i]);
+            acc += z * z + (1.0 / R[i]) * st[(long long)n * DD + (long long)i * D + i];
+        }
+        const double sm = block_sum(acc, sh);
+        double ld = 0.0;
+        for (int i = 0; i < D; ++i) ld += log(sqrt(R[i]));
+        Eobs = 0.5 * (sm + M * (D * LOG2PI + 2.0 * ld));
+    }
+    if (tid == 0) {
+        const double E0 = b.E0[p * b.E0_stride];
+        F[p] = E0 + Esde + Eobs;
+        if (ex.parts != nullptr && lp == 0) {
+            ex.parts[0] = E0;
+            ex.parts[1] = Esde;
+            ex.parts[2] = Eobs;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+template <int D>
+static void fwd_dispatch(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
+                         int count, cudaStream_t st)
+{
+    const int th = 64, bl = (count + th - 1) / th;
+    switch (b.method) {
+    case ODE_EULER: small_fwd_kernel<D, ODE_EULER><<<bl, th, 0, st>>>(b, s, x, xs, p0, count); break;
+    case ODE_HEUN:  small_fwd_kernel<D, ODE_HEUN><<<bl, th, 0, st>>>(b, s, x, xs, p0, count); break;
+    case ODE_RK2:   small_fwd_kernel<D, ODE_RK2><<<bl, th, 0, st>>>(b, s, x, xs, p0, count); break;
+    default:        small_fwd_kernel<D, ODE_RK4><<<bl, th, 0, st>>>(b, s, x, xs, p0, count); break;
+    }
+}
+void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
+                      int count, cudaStream_t st)
+{
+    if (b.D == 1) fwd_dispatch<1>(b, s, x, xs, p0, count, st);
+    else          fwd_dispatch<3>(b, s, x, xs, p0, count, st);
+}
+
+void launch_small_energy(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
+                         int count, const Extra& ex, cudaStream_t st)
+{
+    const long long tot = (long long)count * b.N;
+    const int th = 128;
+    const unsigned bl = (unsigned)((tot + th - 1) / th);
+    if (b.model == MODEL_DW)      small_energy_kernel<MODEL_DW, 1><<<bl, th, 0, st>>>(b, s, x, xs, p0, count, ex);
+    else if (b.model == MODEL_OU) small_energy_kernel<MODEL_OU, 1><<<bl, th, 0, st>>>(b, s, x, xs, p0, count, ex);
+    else                          small_energy_kernel<MODEL_L63, 3><<<bl, th, 0, st>>>(b, s, x, xs, p0, count, ex);
+}
+
+template <int MODEL, int D>
+static void bwd_dispatch(const Batch& b, const Scratch& s, const SmallBwdArgs& a, int p0, int count,
+                         const Extra& ex, cudaStream_t st)
+{
+    const int th = 64, bl = (count + th - 1) / th;
+    switch (b.method) {
+    case ODE_EULER: small_bwd_kernel<MODEL, D, ODE_EULER><<<bl, th, 0, st>>>(b, s, a, p0, count, ex); break;
+    case ODE_HEUN:  small_bwd_kernel<MODEL, D, ODE_HEUN><<<bl, th, 0, st>>>(b, s, a, p0, count, ex); break;
+    case ODE_RK2:   small_bwd_kernel<MODEL, D, ODE_RK2><<<bl, th, 0, st>>>(b, s, a, p0, count, ex); break;
+    default:        small_bwd_kernel<MODEL, D, ODE_RK4><<<bl, th, 0, st>>>(b, s, a, p0, count, ex); break;
+    }
+}
+void launch_small_bwd(const Batch& b, const Scratch& s, const double* x, long long xs, double* g,
+                      long long gs, int p0, int count, const Extra& ex, cudaStream_t st)
+{
+    SmallBwdArgs a{x, xs, g, gs, nullptr, nullptr};
+    if (b.model == MODEL_DW)      bwd_dispatch<MODEL_DW, 1>(b, s, a, p0, count, ex, st);
+    else if (b.model == MODEL_OU) bwd_dispatch<MODEL_OU, 1>(b, s, a, p0, count, ex, st);
+    else                          bwd_dispatch<MODEL_L63, 3>(b, s, a, p0, count, ex, st);
+}
+
+// Stand-alone backward sweep with dense jump tables, any supported D.
+void launch_bwd_dense_l96(int method, int N, double dt, const double* A, const double* dEm,
+                          const double* dEs, const double* jm, const double* js, double* lam,
+                          double* psi, cudaStream_t st);
+void launch_bwd_dense(int method, int D, int N, double dt, const double* A, const double* dEm,
+                      const double* dEs, const double* jm, const double* js, double* lam,
+                      double* psi, cudaStream_t st)
+{
+    if (D == 40) {
+        launch_bwd_dense_l96(method, N, dt, A, dEm, dEs, jm, js, lam, psi, st);
+        return;
+    }
+    Batch b{};
+    b.model = (D == 1) ? MODEL_OU : MODEL_L63;
+    b.method = method; b.D = D; b.N = N; b.B = 1; b.dt = dt; b.dt_model = dt;
+    Scratch s{};
+    s.dEm = const_cast<double*>(dEm);
+    s.dEs = const_cast<double*>(dEs);
+    SmallBwdArgs a{A, 0, nullptr, 0, jm, js};
+    Extra ex{};
+    ex.lamt = lam; ex.psit = psi;
+    if (D == 1) bwd_dispatch<MODEL_OU, 1>(b, s, a, 0, 1, ex, st);
+    else        bwd_dispatch<MODEL_L63, 3>(b, s, a, 0, 1, ex, st);
+}
+
+void launch_finalize(const Batch& b, const Scratch& s, double* F, int p0, int count, const Extra& ex,
+                     cudaStream_t st)
+{
+    finalize_kernel<<<count, 128, 0, st>>>(b, s, F, p0, count, ex);
+}
+
+}  // namespace vgpa

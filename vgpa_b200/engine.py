@@ -1,0 +1,212 @@
+"""
+Batch evaluator: the Python face of a `vgpa_handle` (include/vgpa_b200.h).
+
+One `BatchEvaluator` holds B independent inference problems of the same shape
+(model, ODE method, D, N, observation times) on one GPU and evaluates the
+variational free energy and its gradient for all of them in one call -- what
+`VarGP.free_energy` + `VarGP.gradient` (reference src/var_bayes/variational.py:141-289)
+do for a single problem.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODELS, METHODS, MODEL_DIM, VgpaDesc, VgpaFullOut, dptr, f64, lib, raise_for
+
+
+def _per_problem(a, B, shape, name):
+    """Accept either one array of `shape` (shared) or B of them."""
+    a = f64(a)
+    n = int(np.prod(shape)) if shape else 1
+    if a.size == n:
+        return a.reshape(-1), 0
+    if a.size == B * n:
+        return a.reshape(-1), n
+    raise ValueError(f"{name}: expected {n} or {B}x{n} values, got {a.size}")
+
+
+class BatchEvaluator:
+    """
+    :param model:  "DW" | "OU" | "L63" | "L96"   (simulation.py:20)
+    :param method: "euler" | "heun" | "rk2" | "rk4" (utilities.py:12)
+    :param N: number of time-grid points; dt: sweep step; dt_model: model.time_step
+    :param theta, sigma (D diag), R (D diag), obs_y (M,D), m0 (D), s0 (D,D), E0:
+           one value set shared by the batch, or B of them stacked on axis 0
+    :param obs_t: (M,) sorted unique observation indices, shared by the batch
+    """
+
+    def __init__(self, model, method, N, dt, theta, sigma, R, obs_t, obs_y, m0, s0, E0,
+                 B=1, dt_model=None, device=0, scratch_bytes=0):
+        key = str(model).upper()
+        if key not in MODELS:
+            raise ValueError(f" Unknown stochastic model -> {key}")
+        mkey = str(method).lower()
+        if mkey not in METHODS:
+            raise ValueError(f" Integration method is unknown -> {method}.")
+        D = MODEL_DIM[key]
+        self.model, self.method, self.D, self.N, self.B = key, mkey, D, int(N), int(B)
+        self.n_x = self.N * D * (D + 1)
+        self.device = int(device)
+        obs_t = np.ascontiguousarray(np.asarray(obs_t, dtype=np.int64).ravel())
+        M = obs_t.size
+        nth = 3 if key == "L63" else 1
+        keep = {}
+        d = VgpaDesc()
+        d.model, d.method, d.D, d.N, d.M, d.B = MODELS[key], METHODS[mkey], D, self.N, M, self.B
+        d.device = self.device
+        d.dt = float(dt)
+        d.dt_model = float(dt if dt_model is None else dt_model)
+        for name, val, shape in (("theta", theta, (nth,)), ("sigma", sigma, (D,)), ("R", R, (D,)),
+                                 ("obs_y", obs_y, (M, D)), ("m0", m0, (D,)), ("s0", s0, (D, D)),
+                                 ("E0", E0, ())):
+            if name == "obs_y" and M == 0:
+                continue
+            arr, stride = _per_problem(val, self.B, shape, name)
+            keep[name] = arr
+            setattr(d, name, dptr(arr))
+            setattr(d, name + "_stride", stride)
+        keep["obs_t"] = obs_t
+        d.obs_t = obs_t.ctypes.data_as(C.POINTER(C.c_int64))
+        d.scratch_bytes = int(scratch_bytes)
+        self._h = C.c_void_p()
+        rc = lib.vgpa_create(C.byref(d), C.byref(self._h))
+        raise_for(rc, None)
+        self._keep = keep
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.vgpa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- evaluation ---------------------------------------------------------
+    def eval(self, X, want_grad=True, F_out=None, G_out=None):
+        """Host buffers.  X: (n_x,) shared by all problems, or (B, n_x).
+        Returns (F (B,), grad (B, n_x) or None)."""
+        X = np.asarray(X)
+        if X.dtype != np.float64 or not X.flags.c_contiguous:
+            X = f64(X)
+        if X.size == self.n_x:
+            xs = 0
+        elif X.size == self.B * self.n_x:
+            xs = self.n_x
+        else:
+            raise ValueError(f"x: expected {self.n_x} or {self.B}x{self.n_x} values, got {X.size}")
+        F = np.empty(self.B) if F_out is None else F_out
+        G = None
+        if want_grad:
+            G = np.empty((self.B, self.n_x)) if G_out is None else G_out
+        rc = lib.vgpa_eval(self._h, X.ctypes.data, xs, 1 if want_grad else 0, F.ctypes.data,
+                           G.ctypes.data if want_grad else None, self.n_x)
+        raise_for(rc, self._h)
+        return F, G
+
+    def eval_device(self, x_ptr, x_stride, F_ptr, grad_ptr=None, grad_stride=None, stream=0):
+        """Device pointers (ints), asynchronous on `stream`; call sync() afterwards."""
+        rc = lib.vgpa_eval_device(self._h, x_ptr, x_stride, 1 if grad_ptr else 0, F_ptr, grad_ptr,
+                                  self.n_x if grad_stride is None else grad_stride, stream or None)
+        raise_for(rc, self._h)
+
+    def sync(self):
+        raise_for(lib.vgpa_sync(self._h), self._h)
+
+    def eval_full(self, x, problem=0):
+        """Everything the reference caches or passes between stages, for one problem."""
+        x = f64(x).reshape(-1)
+        if x.size != self.n_x:
+            raise ValueError(f"x: expected {self.n_x} values, got {x.size}")
+        N, D = self.N, self.D
+        nv, nm = N * D, N * D * D
+        bufs = dict(F=np.zeros(1), parts=np.zeros(3), grad=np.empty(self.n_x), mt=np.empty(nv),
+                    st=np.empty(nm), lamt=np.empty(nv), psit=np.empty(nm), Efx=np.empty(nv),
+                    Edf=np.empty(nm), dEsde_dm=np.empty(nv), dEsde_ds=np.empty(nm))
+        out = VgpaFullOut(**{k: dptr(v) for k, v in bufs.items()})
+        rc = lib.vgpa_eval_full(self._h, int(problem), dptr(x), C.byref(out))
+        raise_for(rc, self._h)
+        vs = (N,) if D == 1 else (N, D)
+        ms = (N,) if D == 1 else (N, D, D)
+        res = {k: bufs[k].reshape(ms if k in ("st", "psit", "Edf", "dEsde_ds") else vs)
+               for k in ("mt", "st", "lamt", "psit", "Efx", "Edf", "dEsde_dm", "dEsde_ds")}
+        res.update(F=float(bufs["F"][0]), E0=bufs["parts"][0], Esde=bufs["parts"][1],
+                   Eobs=bufs["parts"][2], grad=bufs["grad"])
+        return res
+
+    # -- introspection ------------------------------------------------------
+    @property
+    def launch_count(self):
+        return int(lib.vgpa_launch_count(self._h))
+
+    @property
+    def chunk_size(self):
+        return int(lib.vgpa_chunk_size(self._h))
+
+    @property
+    def scratch_bytes(self):
+        return int(lib.vgpa_scratch_in_use(self._h))
+
+
+# -- operator-level entry points (one problem, host buffers) -------------------
+def solve_fwd(method, A, b, m0, s0, sigma_diag, dt, device=0):
+    """FwdOde.__call__ (fwd_ode.py:45): returns mt (N,D), st (N,D,D) (1-D: (N,), (N,))."""
+    b = f64(b)
+    single = b.ndim == 1
+    N = b.shape[0]
+    D = 1 if single else b.shape[1]
+    A, m0, s0, sg = f64(A), f64(np.atleast_1d(m0)), f64(np.atleast_1d(s0)), f64(np.atleast_1d(sigma_diag))
+    if A.size != N * D * D or m0.size != D or s0.size != D * D or sg.size != D:
+        raise ValueError("solve_fwd: inconsistent shapes")
+    mt, st = np.empty(N * D), np.empty(N * D * D)
+    rc = lib.vgpa_solve_fwd(device, METHODS[str(method).lower()], D, N, float(dt), dptr(A), dptr(b),
+                            dptr(m0), dptr(s0), dptr(sg), dptr(mt), dptr(st))
+    raise_for(rc, None)
+    return (mt, st) if single else (mt.reshape(N, D), st.reshape(N, D, D))
+
+
+def solve_bwd(method, A, dEsde_dm, dEsde_ds, dEobs_dm, dEobs_ds, dt, device=0):
+    """BwdOde.__call__ (bwd_ode.py:45): returns lam (N,D), psi (N,D,D)."""
+    g = f64(dEsde_dm)
+    single = g.ndim == 1
+    N = g.shape[0]
+    D = 1 if single else g.shape[1]
+    A, G, jm, js = f64(A), f64(dEsde_ds), f64(dEobs_dm), f64(dEobs_ds)
+    if A.size != N * D * D or G.size != N * D * D or jm.size != N * D or js.size != N * D * D:
+        raise ValueError("solve_bwd: inconsistent shapes")
+    lam, psi = np.empty(N * D), np.empty(N * D * D)
+    rc = lib.vgpa_solve_bwd(device, METHODS[str(method).lower()], D, N, float(dt), dptr(A), dptr(g),
+                            dptr(G), dptr(jm), dptr(js), dptr(lam), dptr(psi))
+    raise_for(rc, None)
+    return (lam, psi) if single else (lam.reshape(N, D), psi.reshape(N, D, D))
+
+
+def model_energy(model, theta, sigma_diag, A, b, m, S, dt_model, device=0):
+    """model.energy(A, b, m, S, obs_t) of the reference's StochasticProcess classes.
+    Returns Esde, Ef, Edf, dEsde_dm, dEsde_ds."""
+    key = str(model).upper()
+    D = MODEL_DIM[key]
+    b = f64(b)
+    N = b.shape[0]
+    A, m, S = f64(A), f64(m), f64(S)
+    th, sg = f64(np.atleast_1d(theta)), f64(np.atleast_1d(sigma_diag))
+    if A.size != N * D * D or m.size != N * D or S.size != N * D * D or b.size != N * D or sg.size != D:
+        raise ValueError("model_energy: inconsistent shapes")
+    Esde = np.zeros(1)
+    Ef, Edf, dm, ds = np.empty(N * D), np.empty(N * D * D), np.empty(N * D), np.empty(N * D * D)
+    rc = lib.vgpa_model_energy(device, MODELS[key], D, N, float(dt_model), dptr(th), dptr(sg), dptr(A),
+                               dptr(b), dptr(m), dptr(S), dptr(Esde), dptr(Ef), dptr(Edf), dptr(dm), dptr(ds))
+    raise_for(rc, None)
+    if D == 1:
+        return float(Esde[0]), Ef, Edf, dm, ds
+    return float(Esde[0]), Ef.reshape(N, D), Edf.reshape(N, D, D), dm.reshape(N, D), ds.reshape(N, D, D)
