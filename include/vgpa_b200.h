@@ -154,6 +154,14 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
                       const double *S, double *Esde, double *Ef, double *Edf, double *dEsde_dm,
                       double *dEsde_ds);
 
+/* GaussianLikelihood.__call__ and .gradients (gaussian_like.py:39-243) on their
+ * own: one problem, HOST buffers, identity operator, diagonal R (D values).
+ * Outputs: Eobs (1 value) and the dense jump tables dEobs_dm (N,D),
+ * dEobs_ds (N,D,D), zero except at obs_t. */
+int vgpa_obs_energy(int device, int D, int N, int M, const int64_t *obs_t, const double *obs_y,
+                    const double *R, const double *mt, const double *st, double *Eobs,
+                    double *dEobs_dm, double *dEobs_ds);
+
 /* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
 void *vgpa_host_alloc(int64_t bytes);
 void vgpa_host_free(void *p);
@@ -163,6 +171,13 @@ void vgpa_host_free(void *p);
 int64_t vgpa_launch_count(const vgpa_handle *h);
 int64_t vgpa_chunk_size(const vgpa_handle *h);
 int64_t vgpa_scratch_in_use(const vgpa_handle *h);
+/* Per-kernel device timing for bench.py's roofline: when enabled, every kernel
+ * launch of vgpa_eval / vgpa_eval_device is bracketed by CUDA events on the
+ * launching stream.  vgpa_get_timing synchronises, then returns the accumulated
+ * milliseconds and launch counts per kernel kind and clears the accumulators:
+ *   kind 0 forward sweep, 1 time-parallel energy, 2 finalize (F), 3 backward+gradient. */
+int vgpa_set_timing(vgpa_handle *h, int enable);
+int vgpa_get_timing(vgpa_handle *h, double ms[4], int64_t launches[4]);
 const char *vgpa_version(void);
 
 #ifdef __cplusplus

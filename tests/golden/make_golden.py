@@ -205,6 +205,30 @@ def make_scg(ref, which):
         print(f"{name.name}: it={n} fx={fx:.12g} f_eval={st['f_eval']} ({el:.1f}s)")
 
 
+def make_scg_rosenbrock(ref):
+    """The reference's SCG on an analytic test function (no VGPA involved): pins the
+    repo's own optimiser (vgpa_b200/scg.py) on the CPU."""
+    def f(x):
+        return float(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1.0 - x[:-1]) ** 2))
+
+    def df(x, eval_fun=False):
+        g = np.zeros_like(x)
+        g[:-1] = -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1.0 - x[:-1])
+        g[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+        return g
+    x0 = np.array([-1.2, 1.0, 0.7, -0.4, 1.5, 0.2])
+    scg = ref["SCG"](f, df, {"max_it": 400, "x_tol": 1.0e-10, "f_tol": 1.0e-14, "display": False})
+    with contextlib.redirect_stdout(io.StringIO()):
+        x, fx = scg(x0.copy())
+    st = scg.stats
+    n = int(st["MaxIt"])
+    np.savez_compressed(HERE / "scg_rosenbrock.npz", x0=x0, x_final=x, fx_final=np.float64(fx),
+                        n_it=np.int64(n), trace_fx=st["fx"][:n].copy(), trace_dfx=st["dfx"][:n].copy(),
+                        trace_beta=st["beta"][:n].copy(), f_eval=np.float64(st["f_eval"]),
+                        df_eval=np.float64(st["df_eval"]))
+    print(f"scg_rosenbrock.npz: it={n} fx={fx:.6g}")
+
+
 def make_l96_full(ref):
     """Known answers at the north-star shape (L96 D=40, tf=10 -> N=1001, RK2):
     F(x0), |grad F(x0)| and sparse samples of the gradient.  x0 itself is not
@@ -235,6 +259,7 @@ if __name__ == "__main__":
                     help="also write SCG traces (default: DW OU L63 L96)")
     ap.add_argument("--l96-full", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--rosenbrock", action="store_true")
     a = ap.parse_args()
     ref = _import_reference()
     if not a.no_eval:
@@ -243,4 +268,6 @@ if __name__ == "__main__":
         make_scg(ref, a.scg or ["DW", "OU", "L63", "L96"])
     if a.l96_full:
         make_l96_full(ref)
+    if a.rosenbrock:
+        make_scg_rosenbrock(ref)
     print(json.dumps({"numpy": np.__version__}))

@@ -1,0 +1,91 @@
+"""
+GPU tests through the reference-facing interface (Simulation / VarGP / SCG):
+the SCG convergence trace of the reference, recorded in tests/golden/scg_*.npz with
+the reference's own optimiser, must be reproduced within 1e-6 on the common prefix
+(BASELINE.json), and the known answers at the north-star shape (L96 D=40, N=1001)
+must be matched to 1e-9.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_err
+
+sys.path.insert(0, str(GOLDEN))
+import make_golden as mg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+JOBS = {"DW": ("euler", None), "OU": ("rk4", None), "L63": ("heun", 2.0), "L96": ("rk2", 0.2)}
+
+
+@pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
+def test_scg_trace_matches_reference(model):
+    from vgpa_b200 import SCG, Simulation
+    g = np.load(GOLDEN / f"scg_{model}.npz")
+    method, tf = JOBS[model]
+    sim = Simulation("t")
+    sim.setup(mg.config(model, method, tf))
+    vgpa = sim.build()
+    x0 = vgpa.initialization()
+    assert np.array_equal(x0, g["x"])
+    scg = SCG(vgpa.free_energy, vgpa.gradient,
+              {"max_it": int(g["max_it"]), "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False})
+    x, fx = scg(x0.copy())
+    n_ref, n_new = int(g["n_it"]), int(scg.stats["MaxIt"])
+    n = min(n_ref, n_new)
+    # the stopping iteration may move by a few because of the |f_new - f_old| <= 1e-8 test
+    assert abs(n_ref - n_new) <= max(2, n_ref // 50), (n_ref, n_new)
+    ref, new = g["trace_fx"][:n], scg.stats["fx"][:n]
+    assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6
+    assert abs(fx - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0)
+    # one CUDA evaluation per distinct x: fewer than the reference's f_eval count
+    assert vgpa.n_eval <= float(g["f_eval"])
+    vgpa.close()
+
+
+def test_l96_north_star_known_answers():
+    """L96 D=40, tf=10 (N=1001, T=1000 steps), RK2: F(x0), |grad|, gradient samples."""
+    from vgpa_b200 import Simulation
+    g = np.load(GOLDEN / "known_L96_N1001.npz")
+    sim = Simulation("t")
+    sim.setup(mg.config("L96", "rk2", 10.0))
+    vgpa = sim.build()
+    x0 = vgpa.initialization()
+    assert x0.size == 1001 * 40 * 41
+    assert np.array_equal(x0[g["x0_idx"]], g["x0_samples"]) and x0.sum() == float(g["x0_sum"])
+    F = vgpa.free_energy(x0)
+    grad = vgpa.gradient(x0)
+    assert abs(F - float(g["F_x0"])) <= 1e-9 * abs(float(g["F_x0"]))
+    assert abs(np.linalg.norm(grad) - float(g["gnorm_x0"])) <= 1e-9 * float(g["gnorm_x0"])
+    assert np.abs(grad[g["g_idx"]] - g["g_samples"]).max() <= 1e-9 * float(g["g_absmax"])
+    out = vgpa.arg_out
+    assert out["mt"].shape == (1001, 40) and out["psit"].shape == (1001, 40, 40)
+    assert np.all(out["lamt"][-1] == 0.0) and np.all(out["psit"][-1] == 0.0)
+    vgpa.close()
+
+
+def test_reference_operator_objects_on_gpu():
+    """The level-3 operator objects (FwdOde, BwdOde, model.energy, likelihood) chained
+    by hand as VarGP.free_energy does (variational.py:169-181) give the fused answer."""
+    from vgpa_b200 import Simulation
+    g = np.load(GOLDEN / "eval_L63_rk4.npz")
+    sim = Simulation("t")
+    sim.setup(mg.config("L63", "rk4", 2.0))
+    vgpa = sim.build()
+    N, D = vgpa.dim_n, vgpa.dim_d
+    x = g["x"]
+    A, b = x[:N * D * D].reshape(N, D, D), x[N * D * D:].reshape(N, D)
+    md = sim.m_data
+    mt, st = vgpa.fwd_ode(A, b, md["m0"], md["s0"], md["model"].sigma)
+    Eobs = vgpa.likelihood(mt, st)
+    Esde, (Efx, Edf), (dm, ds, *_) = md["model"].energy(A, b, mt, st, vgpa.obs_t)
+    jm, js, *_ = vgpa.likelihood.gradients(mt, st)
+    lam, psi = vgpa.bwd_ode(A, dm, ds, jm, js)
+    E0 = vgpa.kl0(md["m0"], md["s0"])
+    F = float(E0 + Esde + Eobs)
+    assert abs(F - float(g["F"])) <= 1e-9 * abs(float(g["F"]))
+    assert rel_err(lam, g["lamt"]) < 1e-9 and rel_err(psi, g["psit"]) < 1e-9
+    assert abs(vgpa.free_energy(x) - F) <= 1e-9 * abs(F)
+    vgpa.close()

@@ -1,0 +1,111 @@
+"""
+CPU tests of the host side: the mirror of the reference's interface reproduces the
+reference's problem set-up bit for bit (same numpy Generator stream), the repo's
+SCG reproduces the reference optimiser's trace on an analytic function, the C-ABI
+library loads and exports every symbol include/vgpa_b200.h declares, and argument
+errors surface as the reference's exception types.  No CUDA compute here.
+"""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+sys.path.insert(0, str(GOLDEN))
+import make_golden as mg  # noqa: E402  (only its config() helper: the reference itself is not imported)
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "vgpa_b200.h").read_text()
+    declared = set(re.findall(r"\b(vgpa_[a-z_0-9]+)\s*\(", header))
+    declared -= {"vgpa_handle"}
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(str(ROOT / "vgpa_b200" / "libvgpa_b200.so"))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.vgpa_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.vgpa_version()
+
+
+def test_create_validates_before_touching_the_device():
+    """ValueError-class failures are reported without a GPU (validation precedes CUDA)."""
+    from vgpa_b200.engine import BatchEvaluator
+    base = dict(model="OU", method="rk4", N=11, dt=0.01, theta=[2.0], sigma=[0.8], R=[0.04],
+                obs_t=[3, 6], obs_y=np.zeros((2, 1)), m0=[0.0], s0=[[0.2]], E0=0.0)
+    for bad in (dict(model="XX"), dict(method="leapfrog"), dict(dt=-1.0), dict(sigma=[-0.8]),
+                dict(N=1), dict(obs_t=[6, 3]), dict(obs_t=[3, 11])):
+        with pytest.raises(ValueError):
+            BatchEvaluator(**{**base, **bad})
+
+
+@pytest.mark.parametrize("model,method,tf", [("DW", "euler", 10.0), ("OU", "rk4", 10.0),
+                                              ("L63", "rk2", 2.0), ("L96", "rk2", 0.2)])
+def test_setup_reproduces_reference_problem(model, method, tf):
+    """Simulation.setup + VarGP.initialization give the reference's obs_t, obs_y, m0, x0."""
+    from vgpa_b200.simulation import Simulation
+    g = np.load(GOLDEN / f"eval_{model}_{method}.npz")
+    sim = Simulation("t")
+    sim.setup(mg.config(model, method, tf))
+    md = sim.m_data
+    assert np.array_equal(md["obs_t"], g["obs_t"])
+    assert np.array_equal(np.asarray(md["obs_y"]).ravel(), g["obs_y"].ravel())
+    assert np.array_equal(np.atleast_1d(md["m0"]), g["m0"])
+    vgpa = sim.build()
+    assert vgpa.dim_n == int(g["N"]) and vgpa.dim_d == int(g["D"])
+    assert np.array_equal(vgpa.initialization(), g["x0"])
+    assert float(vgpa.dt) == float(np.abs(md["model"].time_window[1] - md["model"].time_window[0]))
+
+
+def test_prior_kl0_matches_reference_values():
+    from vgpa_b200.prior import PriorKL0
+    for name in ("eval_DW_euler", "eval_L63_rk2", "eval_L96_rk2"):
+        g = np.load(GOLDEN / f"{name}.npz")
+        D = int(g["D"])
+        if D == 1:
+            k = PriorKL0(float(g["mu0"][0]), float(g["tau0"][0, 0]), True)(float(g["m0"][0]), float(g["s0"][0, 0]))
+        else:
+            k = PriorKL0(g["mu0"], g["tau0"], False)(g["m0"], g["s0"])
+        assert abs(k - float(g["E0"])) <= 1e-13 * abs(float(g["E0"]))
+
+
+def test_scg_reproduces_reference_trace_on_rosenbrock():
+    from vgpa_b200.scg import SCG
+    g = np.load(GOLDEN / "scg_rosenbrock.npz")
+
+    def f(x):
+        return float(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1.0 - x[:-1]) ** 2))
+
+    def df(x, eval_fun=False):
+        gr = np.zeros_like(x)
+        gr[:-1] = -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1.0 - x[:-1])
+        gr[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+        return gr
+    scg = SCG(f, df, {"max_it": 400, "x_tol": 1.0e-10, "f_tol": 1.0e-14, "display": False})
+    x, fx = scg(g["x0"].copy())
+    n = int(scg.stats["MaxIt"])
+    assert n == int(g["n_it"])
+    assert np.array_equal(scg.stats["fx"][:n], g["trace_fx"])
+    assert np.array_equal(scg.stats["beta"][:n], g["trace_beta"])
+    assert np.array_equal(scg.stats["dfx"][:n], g["trace_dfx"])
+    assert scg.stats["f_eval"] == float(g["f_eval"]) and scg.stats["df_eval"] == float(g["df_eval"])
+    assert np.array_equal(x, g["x_final"]) and fx == float(g["fx_final"])
+
+
+def test_reference_style_errors():
+    from vgpa_b200 import DoubleWell, FwdOde, Lorenz96, Simulation
+    with pytest.raises(ValueError):
+        FwdOde(-0.01, "euler")
+    with pytest.raises(ValueError):
+        FwdOde(0.01, "leapfrog")
+    with pytest.raises(ValueError):
+        DoubleWell(-1.0, 1.0)
+    with pytest.raises(ValueError):
+        Lorenz96([4.0] * 40, 8.0, dim_d=8)
+    with pytest.raises(NotImplementedError):
+        DoubleWell(0.8, 1.0).sample_path
+    with pytest.raises(ValueError):
+        Simulation("x").setup({**mg.config("DW", "euler"), "Model": "nope"})

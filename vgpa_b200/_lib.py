@@ -70,6 +70,8 @@ def _load():
     lib.vgpa_solve_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 7
     lib.vgpa_model_energy.restype = C.c_int
     lib.vgpa_model_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 11
+    lib.vgpa_obs_energy.restype = C.c_int
+    lib.vgpa_obs_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip] + [_dp] * 7
     lib.vgpa_host_alloc.restype = C.c_void_p
     lib.vgpa_host_alloc.argtypes = [C.c_int64]
     lib.vgpa_host_free.restype = None
@@ -80,6 +82,10 @@ def _load():
     lib.vgpa_chunk_size.argtypes = [H]
     lib.vgpa_scratch_in_use.restype = C.c_int64
     lib.vgpa_scratch_in_use.argtypes = [H]
+    lib.vgpa_set_timing.restype = C.c_int
+    lib.vgpa_set_timing.argtypes = [H, C.c_int]
+    lib.vgpa_get_timing.restype = C.c_int
+    lib.vgpa_get_timing.argtypes = [H, _dp, _ip]
     lib.vgpa_version.restype = C.c_char_p
     return lib
 

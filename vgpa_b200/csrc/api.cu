@@ -57,6 +57,29 @@ struct vgpa_handle {
     bool status_dirty = false;
     long long launches = 0;
     std::string err;
+    // optional per-kernel timing (bench.py roofline)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev[4];
+    size_t tev_used[4] = {0, 0, 0, 0};
+    double t_ms[4] = {0, 0, 0, 0};
+    long long t_n[4] = {0, 0, 0, 0};
+
+    void tick(int kind, cudaStream_t st, bool begin)
+    {
+        if (!timing) return;
+        if (begin) {
+            if (tev_used[kind] == tev[kind].size()) {
+                cudaEvent_t a, b;
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                tev[kind].push_back({a, b});
+            }
+            cudaEventRecord(tev[kind][tev_used[kind]].first, st);
+        } else {
+            cudaEventRecord(tev[kind][tev_used[kind]].second, st);
+            ++tev_used[kind];
+        }
+    }
 
     int fail(int code, const char* fmt, ...)
     {
@@ -107,24 +130,25 @@ void run_chunk(vgpa_handle* h, const double* d_x, long long xs, int want_grad, d
     Scratch sc = h->scratch;
     sc.status = h->status.as<int>() + p0;
     const Batch& b = h->batch;
-    if (small_model(b.model)) {
-        launch_small_fwd(b, sc, d_x, xs, p0, count, st);
-        launch_small_energy(b, sc, d_x, xs, p0, count, ex, st);
-        launch_finalize(b, sc, d_F, p0, count, ex, st);
-        h->launches += 3;
-        if (want_grad) {
-            launch_small_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
-            h->launches += 1;
-        }
-    } else {
-        launch_l96_fwd(b, sc, d_x, xs, p0, count, st);
-        launch_l96_energy(b, sc, d_x, xs, p0, count, ex, st);
-        launch_finalize(b, sc, d_F, p0, count, ex, st);
-        h->launches += 3;
-        if (want_grad) {
-            launch_l96_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
-            h->launches += 1;
-        }
+    const bool small = small_model(b.model);
+    h->tick(0, st, true);
+    if (small) launch_small_fwd(b, sc, d_x, xs, p0, count, st);
+    else launch_l96_fwd(b, sc, d_x, xs, p0, count, st);
+    h->tick(0, st, false);
+    h->tick(1, st, true);
+    if (small) launch_small_energy(b, sc, d_x, xs, p0, count, ex, st);
+    else launch_l96_energy(b, sc, d_x, xs, p0, count, ex, st);
+    h->tick(1, st, false);
+    h->tick(2, st, true);
+    launch_finalize(b, sc, d_F, p0, count, ex, st);
+    h->tick(2, st, false);
+    h->launches += 3;
+    if (want_grad) {
+        h->tick(3, st, true);
+        if (small) launch_small_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
+        else launch_l96_bwd(b, sc, d_x, xs, d_grad, gs, p0, count, ex, st);
+        h->tick(3, st, false);
+        h->launches += 1;
     }
 }
 
@@ -296,6 +320,11 @@ void vgpa_destroy(vgpa_handle* h)
         if (h->ev_comp[q]) cudaEventDestroy(h->ev_comp[q]);
         if (h->ev_d2h[q]) cudaEventDestroy(h->ev_d2h[q]);
     }
+    for (int k = 0; k < 4; ++k)
+        for (auto& pr : h->tev[k]) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -626,6 +655,63 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
     return VGPA_OK;
 }
 
+int vgpa_obs_energy(int device, int D, int N, int M, const int64_t* obs_t, const double* obs_y, const double* R,
+                    const double* mt, const double* st, double* Eobs, double* jm, double* js)
+{
+    if ((D != 1 && D != 3 && D != 40) || N < 2 || M < 0 || M > N) { g_create_error = "Wrong dimensions for the likelihood"; return VGPA_EINVAL; }
+    if ((M > 0 && (!obs_t || !obs_y)) || !R || !mt || !st || !Eobs || !jm || !js) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    for (int n = 0; n < M; ++n)
+        if (obs_t[n] < 0 || obs_t[n] >= N) { g_create_error = "observation index out of range"; return VGPA_EINVAL; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const long long nv = (long long)N * D, nm = (long long)N * D * D;
+    DevBuf dot, doy, dR, dmt, dst, djm, djs, des, dparts, dzero, dF;
+    auto cleanup = [&]() { for (DevBuf* q : {&dot, &doy, &dR, &dmt, &dst, &djm, &djs, &des, &dparts, &dzero, &dF}) q->release(); };
+    std::vector<long long> ot(std::max(M, 1), 0);
+    for (int n = 0; n < M; ++n) ot[n] = obs_t[n];
+    cudaError_t e;
+    if ((e = dot.alloc(sizeof(long long) * ot.size())) != cudaSuccess || (e = doy.alloc(sizeof(double) * std::max(M, 1) * D)) != cudaSuccess ||
+        (e = dR.alloc(sizeof(double) * D)) != cudaSuccess || (e = dmt.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = dst.alloc(sizeof(double) * nm)) != cudaSuccess || (e = djm.alloc(sizeof(double) * nv)) != cudaSuccess ||
+        (e = djs.alloc(sizeof(double) * nm)) != cudaSuccess || (e = des.alloc(sizeof(double) * N)) != cudaSuccess ||
+        (e = dparts.alloc(sizeof(double) * 3)) != cudaSuccess || (e = dzero.alloc(sizeof(double))) != cudaSuccess ||
+        (e = dF.alloc(sizeof(double))) != cudaSuccess ||
+        (e = cudaMemset(dzero.p, 0, sizeof(double))) != cudaSuccess || (e = cudaMemset(des.p, 0, sizeof(double) * N)) != cudaSuccess ||
+        (e = cudaMemcpy(dot.p, ot.data(), sizeof(long long) * ot.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (M > 0 && (e = cudaMemcpy(doy.p, obs_y, sizeof(double) * M * D, cudaMemcpyHostToDevice)) != cudaSuccess) ||
+        (e = cudaMemcpy(dR.p, R, sizeof(double) * D, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dmt.p, mt, sizeof(double) * nv, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dst.p, st, sizeof(double) * nm, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_obs_energy: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    Batch bt{};
+    bt.model = (D == 1) ? MODEL_OU : (D == 3 ? MODEL_L63 : MODEL_L96);
+    bt.D = D; bt.N = N; bt.M = M; bt.B = 1; bt.dt = 1.0; bt.dt_model = 1.0;
+    bt.sigma = dR.as<double>(); bt.R = dR.as<double>(); bt.E0 = dzero.as<double>();
+    bt.obs_t = dot.as<long long>(); bt.obs_y = doy.as<double>();
+    Scratch sc{};
+    sc.mt = dmt.as<double>(); sc.st = dst.as<double>(); sc.esde_t = des.as<double>();
+    Extra ex{};
+    ex.parts = dparts.as<double>();
+    launch_finalize(bt, sc, dF.as<double>(), 0, 1, ex, nullptr);
+    launch_jump_tables(D, N, M, dot.as<long long>(), doy.as<double>(), dR.as<double>(), dmt.as<double>(),
+                       djm.as<double>(), djs.as<double>(), nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    double parts[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(parts, dparts.p, sizeof parts, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(jm, djm.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(js, djs.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA error in vgpa_obs_energy: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    *Eobs = parts[2];
+    return VGPA_OK;
+}
+
 void* vgpa_host_alloc(int64_t bytes)
 {
     void* p = nullptr;
@@ -635,6 +721,35 @@ void* vgpa_host_alloc(int64_t bytes)
 void vgpa_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
+}
+
+int vgpa_set_timing(vgpa_handle* h, int enable)
+{
+    if (!h) return VGPA_EINVAL;
+    h->timing = enable != 0;
+    return VGPA_OK;
+}
+
+int vgpa_get_timing(vgpa_handle* h, double ms[4], int64_t launches[4])
+{
+    if (!h || !ms || !launches) return VGPA_EINVAL;
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    for (int k = 0; k < 4; ++k) {
+        for (size_t q = 0; q < h->tev_used[k]; ++q) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, h->tev[k][q].first, h->tev[k][q].second) == cudaSuccess) {
+                h->t_ms[k] += t;
+                h->t_n[k] += 1;
+            }
+        }
+        h->tev_used[k] = 0;
+        ms[k] = h->t_ms[k];
+        launches[k] = h->t_n[k];
+        h->t_ms[k] = 0;
+        h->t_n[k] = 0;
+    }
+    return VGPA_OK;
 }
 
 int64_t vgpa_launch_count(const vgpa_handle* h) { return h ? h->launches : 0; }

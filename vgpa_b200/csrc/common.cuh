@@ -71,4 +71,8 @@ void launch_bwd_dense(int method, int D, int N, double dt, const double* A, cons
                       const double* dEs, const double* jm, const double* js, double* lam,
                       double* psi, cudaStream_t st);
 
+// Dense jump tables dEobs_dm (N,D), dEobs_ds (N,D,D) (GaussianLikelihood.gradients).
+void launch_jump_tables(int D, int N, int M, const long long* obs_t, const double* obs_y, const double* R,
+                        const double* mt, double* jm, double* js, cudaStream_t st);
+
 }  // namespace vgpa

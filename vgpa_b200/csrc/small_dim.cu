@@ -723,6 +723,26 @@ void launch_bwd_dense(int method, int D, int N, double dt, const double* A, cons
     else        bwd_dispatch<MODEL_L63, 3>(b, s, a, 0, 1, ex, st);
 }
 
+// gaussian_like.py:188,191 (1-D) / :235,238 (n-D, H = I, diagonal R)
+__global__ void jump_tables_kernel(int D, int N, int M, const long long* __restrict__ obs_t,
+                                   const double* __restrict__ obs_y, const double* __restrict__ R,
+                                   const double* __restrict__ mt, double* __restrict__ jm, double* __restrict__ js)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M * D) return;
+    const int n = q / D, i = q % D;
+    const long long t = obs_t[n];
+    jm[t * D + i] = -(obs_y[(long long)n * D + i] - mt[t * D + i]) / R[i];
+    js[t * D * D + (long long)i * D + i] = 0.5 / R[i];
+}
+void launch_jump_tables(int D, int N, int M, const long long* obs_t, const double* obs_y, const double* R,
+                        const double* mt, double* jm, double* js, cudaStream_t st)
+{
+    cudaMemsetAsync(jm, 0, sizeof(double) * (size_t)N * D, st);
+    cudaMemsetAsync(js, 0, sizeof(double) * (size_t)N * D * D, st);
+    if (M > 0) jump_tables_kernel<<<(M * D + 127) / 128, 128, 0, st>>>(D, N, M, obs_t, obs_y, R, mt, jm, js);
+}
+
 void launch_finalize(const Batch& b, const Scratch& s, double* F, int p0, int count, const Extra& ex,
                      cudaStream_t st)
 {

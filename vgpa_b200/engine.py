@@ -144,6 +144,16 @@ class BatchEvaluator:
                    Eobs=bufs["parts"][2], grad=bufs["grad"])
         return res
 
+    def set_timing(self, enable=True):
+        raise_for(lib.vgpa_set_timing(self._h, 1 if enable else 0), self._h)
+
+    def get_timing(self):
+        """{kind: (total_ms, launches)} since the last call; kinds fwd/energy/finalize/bwd."""
+        ms = np.zeros(4)
+        n = np.zeros(4, dtype=np.int64)
+        raise_for(lib.vgpa_get_timing(self._h, dptr(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), self._h)
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("fwd", "energy", "finalize", "bwd"))}
+
     # -- introspection ------------------------------------------------------
     @property
     def launch_count(self):
@@ -210,3 +220,24 @@ def model_energy(model, theta, sigma_diag, A, b, m, S, dt_model, device=0):
     if D == 1:
         return float(Esde[0]), Ef, Edf, dm, ds
     return float(Esde[0]), Ef.reshape(N, D), Edf.reshape(N, D, D), dm.reshape(N, D), ds.reshape(N, D, D)
+
+
+def obs_energy(obs_t, obs_y, R_diag, m, s, device=0):
+    """GaussianLikelihood.__call__ / .gradients: returns Eobs, dEobs_dm, dEobs_ds."""
+    m = f64(m)
+    single = m.ndim == 1
+    N = m.shape[0]
+    D = 1 if single else m.shape[1]
+    s, oy, R = f64(s), f64(obs_y), f64(np.atleast_1d(R_diag))
+    ot = np.ascontiguousarray(np.asarray(obs_t, dtype=np.int64).ravel())
+    M = ot.size
+    if s.size != N * D * D or oy.size != M * D or R.size != D:
+        raise ValueError("obs_energy: inconsistent shapes")
+    E = np.zeros(1)
+    jm, js = np.empty(N * D), np.empty(N * D * D)
+    rc = lib.vgpa_obs_energy(device, D, N, M, ot.ctypes.data_as(C.POINTER(C.c_int64)), dptr(oy), dptr(R),
+                             dptr(m), dptr(s), dptr(E), dptr(jm), dptr(js))
+    raise_for(rc, None)
+    if single:
+        return float(E[0]), jm, js
+    return float(E[0]), jm.reshape(N, D), js.reshape(N, D, D)

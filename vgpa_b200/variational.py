@@ -1,0 +1,132 @@
+"""
+VarGP: drop-in for the reference's src/var_bayes/variational.py:6-336.
+
+Same constructor, same `initialization()`, `free_energy(x)`, `gradient(x, eval_fun)`
+and `arg_out`, and the same calling protocol the SCG optimiser relies on
+(optim_scg.py:99-100,167,189,234-235).  free_energy and gradient are computed by
+ONE batched CUDA evaluation (B = 1 here) through the C ABI; the gradient of the
+last x is cached so that `f(x)` followed by `df(x)` costs one evaluation instead
+of the reference's two.  There is no CPU path.
+"""
+import numpy as np
+from scipy.interpolate import CubicSpline
+
+from .engine import BatchEvaluator
+
+
+def _diag(a, what):
+    a = np.asarray(a, dtype=float)
+    if a.ndim == 2:
+        if np.count_nonzero(a - np.diag(np.diagonal(a))):
+            raise ValueError(f" VarGP: the CUDA path supports a diagonal {what} only.")
+        return np.diagonal(a).copy()
+    return np.atleast_1d(a)
+
+
+class VarGP(object):
+
+    def __init__(self, model, m0, s0, fwd_ode, bwd_ode, likelihood, kl0, obs_y, obs_t, device=0):
+        self.model = model
+        self.fwd_ode, self.bwd_ode = fwd_ode, bwd_ode
+        self.kl0, self.likelihood = kl0, likelihood
+        self.obs_y, self.obs_t = obs_y, obs_t
+        self.dt = self.model.time_step                           # variational.py:57
+        if self.model.single_dim:
+            self.dim_n, self.dim_d = self.model.sample_path.size, 1
+        else:
+            self.dim_n, self.dim_d = self.model.sample_path.shape
+        self.dim_tot = self.dim_n * self.dim_d * self.dim_d
+        self.output = {"m0": m0, "s0": s0}
+        if str(fwd_ode.method).lower() != str(bwd_ode.method).lower() or fwd_ode.dt != bwd_ode.dt:
+            raise ValueError(" VarGP: forward and backward sweeps must share method and step.")
+        self._device = device
+        self._ev_obj = None
+        self._x_cached = None
+        self._f_cached = None
+        self._g_cached = None
+        self._full_for = None
+        self.n_eval = 0
+
+    @property
+    def _ev(self):
+        """The CUDA handle, created on first use (so that set-up code runs without a GPU)."""
+        if self._ev_obj is None:
+            D = self.dim_d
+            m0, s0 = self.output["m0"], self.output["s0"]
+            self._ev_obj = BatchEvaluator(
+                model=self.model.model_key, method=self.fwd_ode.method, N=self.dim_n, dt=self.fwd_ode.dt,
+                theta=np.atleast_1d(np.asarray(self.model.theta, dtype=float)),
+                sigma=_diag(self.model.sigma, "system noise"),
+                R=_diag(self.likelihood.noise, "observation noise"),
+                obs_t=np.asarray(self.obs_t, dtype=np.int64),
+                obs_y=np.asarray(self.obs_y, dtype=float).reshape(-1, D),
+                m0=np.atleast_1d(np.asarray(m0, dtype=float)),
+                s0=np.asarray(s0, dtype=float).reshape(D, D),
+                E0=float(np.asarray(self.kl0(m0, s0))),              # constant: variational.py:183-185
+                B=1, dt_model=float(self.dt), device=self._device)
+        return self._ev_obj
+
+    # -- variational.py:73-139 (host-side set-up, not on the per-iteration path) ------
+    def initialization(self):
+        time_window = self.model.time_window
+        time_x = [time_window[0], *time_window[self.obs_t], time_window[-1]]
+        if self.model.single_dim:
+            obs_z = np.hstack((self.obs_y[0], self.obs_y, self.obs_y[-1]))
+            a0 = 0.5 * (self.model.sigma / 0.25) * np.ones(self.dim_n)
+            b0 = CubicSpline(time_x, obs_z)(time_window)
+        else:
+            obs_z = np.vstack((self.obs_y[0], self.obs_y, self.obs_y[-1]))
+            mt0 = CubicSpline(time_x, obs_z)(time_window)
+            a0 = np.zeros((self.dim_n, self.dim_d, self.dim_d))
+            b0 = np.zeros((self.dim_n, self.dim_d))
+            s0 = 0.25 * np.eye(self.dim_d)
+            dmt0 = np.diff(mt0, axis=0) / self.dt
+            diag_k = np.diag(self.model.sigma.diagonal() / s0.diagonal())
+            for k in range(self.dim_n - 1):
+                a0[k] = 0.5 * diag_k
+                b0[k] = dmt0[k] + a0[k].diagonal() * mt0[k]
+            a0[-1] = 0.5 * diag_k
+            b0[-1] = a0[-1].diagonal() * mt0[-1]
+        return np.concatenate((a0.ravel(), b0.ravel()))
+
+    # -- the hot path -------------------------------------------------------------------
+    def _evaluate(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        F, G = self._ev.eval(x, want_grad=True)
+        self.n_eval += 1
+        self._x_cached = x.copy()
+        self._f_cached = float(F[0])
+        self._g_cached = G[0]
+        self._full_for = None
+
+    def _is_cached(self, x):
+        return self._x_cached is not None and x.size == self._x_cached.size and \
+            np.array_equal(np.asarray(x).reshape(-1), self._x_cached)
+
+    def free_energy(self, x):
+        """E0 + Esde + Eobs as a Python float (variational.py:141-200)."""
+        if not self._is_cached(x):
+            self._evaluate(x)
+        return self._f_cached
+
+    def gradient(self, x, eval_fun=False):
+        """[dL/dA | dL/db] (variational.py:202-289).  `eval_fun=True` asks for a
+        consistent state at a new x; the cache makes that automatic."""
+        if not self._is_cached(x):
+            self._evaluate(x)
+        return self._g_cached.copy()
+
+    @property
+    def arg_out(self):
+        """m0, s0, mt, st, Efx, Edf, lamt, psit of the last evaluated x (variational.py:292)."""
+        if self._x_cached is not None and self._full_for is None:
+            full = self._ev.eval_full(self._x_cached)
+            for k in ("mt", "st", "Efx", "Edf", "lamt", "psit"):
+                self.output[k] = full[k]
+            self._full_for = True
+        return self.output
+
+    def close(self):
+        if self._ev_obj is not None:
+            self._ev_obj.close()
+            self._ev_obj = None
