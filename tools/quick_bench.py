@@ -26,6 +26,7 @@ def main(B=296, N=1001, method="rk2", steps=3, model="L96"):
         for _ in range(2):
             ev.eval_device(X.data_ptr(), n, F.data_ptr(), G.data_ptr() if want_grad else None, n, st)
         ev.sync()
+        ev.set_timing(True); ev.get_timing()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -33,9 +34,11 @@ def main(B=296, N=1001, method="rk2", steps=3, model="L96"):
         e1.record()
         ev.sync()
         ms = e0.elapsed_time(e1) / steps
+        tm = {k: round(v[0] / max(v[1], 1), 3) for k, v in ev.get_timing().items()}
+        ev.set_timing(False)
         print(json.dumps({"model": model, "B": B, "N": N, "method": method, "want_grad": want_grad,
                           "ms": round(ms, 3), "evals_per_s": round(B / ms * 1e3, 1),
-                          "chunk": ev.chunk_size, "F0": float(F[0])}))
+                          "chunk": ev.chunk_size, "kernel_ms": tm, "F0": float(F[0])}))
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 296

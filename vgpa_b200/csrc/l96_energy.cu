@@ -1,6 +1,6 @@
 // l96_energy.cu -- time-parallel stage of the Lorenz-96 (D = 40) free energy:
 // Esde(t), dEsde/dm(t), dEsde/dS(t) for every (problem, time index) pair, one CTA
-// of 128 threads per pair.
+// of 128 threads (4 warps) per pair.
 //
 // The reference evaluates these with the unscented transform over 2D+1 = 81 sigma
 // points (lorenz_96.py:389-418, utilities.py:239-310, variational.py:339-400),
@@ -17,6 +17,16 @@
 // ut_approx (utilities.py:302-306) is not formed.
 // l96() on the 81 x 40 sigma-point matrix uses numba's FLATTENED np.roll
 // (lorenz_96.py:27-32,85-101): neighbours wrap across adjacent sigma points.
+//
+// Blocked algorithm on 8 x 8 tiles (5 x 5 tile grid), bulk work on the FP64 tensor
+// cores (mma.sync m8n8k4 f64, SASS DMMA):
+//   for k = 0..4:  (a) 8 x 8 diagonal block: L_kk, T_kk = L_kk^-1 by one warp, rows in
+//                      registers, pivots exchanged with shuffles (no square roots inside
+//                      the loop: LDL^T, scaled at the end)
+//                  (b) panel L_ik = C_ik T_kk^T (i > k) and V_kj = T_kk R_kj (j < k): 4 tiles
+//                  (c) trailing C_ij -= L_ik L_jk^T and R_ij -= L_ik V_kj
+//   A L in place over A;  81 residual energies with warp-shuffle reductions;
+//   V^T diag(d) V on the lower tiles, mirrored on store.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,37 +34,105 @@ namespace vgpa {
 namespace {
 
 constexpr int D = 40;
-constexpr int P = 42;
+constexpr int P = 44;               // pitch (doubles): DMMA fragment loads conflict-free
 constexpr int MAT = D * P;
 constexpr int ROWB = D * 8;
 constexpr int K = 2 * D + 1;        // sigma points
 constexpr int TOT = K * D;          // flattened sigma-point matrix
 constexpr int NTH = 128;
-constexpr int NPOS = D * (D + 1) / 2;             // lower-triangle positions
-constexpr int PER = (NPOS + NTH - 1) / NTH;       // positions owned per thread (7)
+constexpr int NB = 5;               // 8 x 8 tile grid
 
 struct EnSmem {
-    double Sb[MAT];   // S(t); later A L
-    double Lb[MAT];   // L = chol(c S), upper triangle zero
-    double Wb[MAT];   // V = L^-1,       upper triangle zero
-    double Ab[MAT];   // A(t)
-    double col[2][D], wrow[2][D];   // pivot panels of the factorisation
-    double mv[D], bv[D], Am[D], isg[D], dvec[D], rs[D], qv[D], dv[D];
+    double Cb[MAT];   // c S -> L (lower block triangle; upper tiles keep stale data, never read)
+    double Wb[MAT];   // R -> V = L^-1 (lower block triangle, zero elsewhere)
+    double Ab[MAT];   // A(t) -> A L
+    double mv[D], bv[D], Am[D], isg[D], qv[D], dv[D];
     double var[K + 3];
     double esde;
     uint64_t bar;
     int bad;
 };
 
-// sigma point matrix entry at flattened index q (row k = q / D, column i = q % D)
-__device__ __forceinline__ double chi_at(const EnSmem& sm, int q)
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 {
-    const int k = q / D, i = q - k * D;
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// sigma point matrix entry at flattened index f (row k = f / D, column i = f % D)
+__device__ __forceinline__ double chi_at(const EnSmem& sm, int f)
+{
+    const int k = f / D, i = f - k * D;
     const double m = sm.mv[i];
     if (k == 0) return m;
-    if (k <= D) return m + sm.Lb[i * P + (k - 1)];
-    return m - sm.Lb[i * P + (k - 1 - D)];
+    const int col = (k <= D) ? k - 1 : k - 1 - D;
+    const double l = (col <= i) ? sm.Cb[i * P + col] : 0.0;   // L is lower triangular
+    return (k <= D) ? m + l : m - l;
 }
+
+// ---- (a) diagonal 8 x 8 block: C_kk -> L_kk (into Cb) and T_kk = L_kk^-1 (into Wb) ----
+// one warp; lane r < 8 owns row r of the block in registers
+__device__ __forceinline__ void factor_diag(EnSmem& sm, int k, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int r = lane & 7;
+    double c[8], wv[8], dd[8];
+    const double* src = &sm.Cb[(8 * k + r) * P + 8 * k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        c[j] = src[j];
+        wv[j] = (j == r) ? 1.0 : 0.0;
+    }
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double pj = __shfl_sync(FULL, c[j], j);   // pivot D_j
+        bad |= !(pj > 0.0);
+        dd[j] = pj;
+        const double lrj = c[j] * (1.0 / pj);            // unit-lower factor entry (rows r > j)
+#pragma unroll
+        for (int kx = j + 1; kx < 8; ++kx) {
+            const double ckj = __shfl_sync(FULL, c[j], kx);   // C[kx][j], unscaled
+            c[kx] = fma(-lrj, ckj, c[kx]);
+        }
+#pragma unroll
+        for (int kx = 0; kx <= j; ++kx) {
+            const double wjk = __shfl_sync(FULL, wv[kx], j);  // W[j][kx]
+            if (r > j) wv[kx] = fma(-lrj, wjk, wv[kx]);
+        }
+    }
+    if (bad && lane == 0) sm.bad = 1;
+    // scale: L = Lt D^1/2, T = D^-1/2 Lt^-1
+    double dr = dd[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) dr = (r == j) ? dd[j] : dr;
+    const double my_rs = 1.0 / sqrt(dr);   // one square root per lane, exchanged below
+    double rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rs[j] = __shfl_sync(FULL, my_rs, j);
+    if (lane < 8) {
+        double* lo = &sm.Cb[(8 * k + r) * P + 8 * k];
+        double* to = &sm.Wb[(8 * k + r) * P + 8 * k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            lo[j] = (j < r) ? c[j] * rs[j] : (j == r ? dd[j] * rs[j] : 0.0);
+            to[j] = (j <= r) ? wv[j] * rs[r] : 0.0;
+        }
+    }
+}
+
+// one 8x8x8 tile product accumulate: acc += sum_{kk<8} Aop[m][kk] * Bop[kk][n]
+// afun(kk) returns A[m=g][kk] for this lane's kk = h*4+q ; bfun(kk) returns B[kk][n=g]
+#define TILE_MMA(acc0, acc1, AEXPR, BEXPR)                    \
+    do {                                                      \
+        _Pragma("unroll") for (int h = 0; h < 2; ++h) {       \
+            const int kk = 4 * h + q;                         \
+            const double a_ = (AEXPR);                        \
+            const double b_ = (BEXPR);                        \
+            dmma(acc0, acc1, a_, b_);                         \
+        }                                                     \
+    } while (0)
 
 __global__ void __launch_bounds__(NTH)
 l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count, Extra ex)
@@ -62,6 +140,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnSmem& sm = *reinterpret_cast<EnSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
     const int N = b.N;
     const int lp = blockIdx.x / N, t = blockIdx.x - lp * N, p = p0 + lp;
     const double* At = x + (long long)p * xs + (long long)t * D * D;
@@ -82,7 +161,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         if (lane == 0) mbar_arrive_expect_tx(&sm.bar, 2 * D * ROWB + 2 * ROWB);
         __syncwarp();
         for (int i = lane; i < D; i += 32) {
-            bulk_g2s(sm.Sb + i * P, St + i * D, ROWB, &sm.bar);
+            bulk_g2s(sm.Cb + i * P, St + i * D, ROWB, &sm.bar);
             bulk_g2s(sm.Ab + i * P, At + i * D, ROWB, &sm.bar);
         }
         if (lane == 0) {
@@ -91,24 +170,14 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         }
     }
     if (tid < D) sm.isg[tid] = 1.0 / b.sigma[p * b.sigma_stride + tid];
-    // decode the lower-triangle positions this thread owns: e = i (i + 1) / 2 + k
-    int pi[PER], pk[PER];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int e = tid + q * NTH;
-        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        pi[q] = (e < NPOS) ? i : -1;
-        pk[q] = e - i * (i + 1) / 2;
-    }
+    for (int e = tid; e < MAT; e += NTH) sm.Wb[e] = 0.0;
     mbar_wait(&sm.bar, 0u);
 
     // <f>, <df/dx> for vgpa_eval_full (lorenz_96.py:34-83,440-462); S is still intact
     if (ex.Efx != nullptr && lp == 0) {
         for (int i = tid; i < D; i += NTH) {
             const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
-            ex.Efx[(long long)t * D + i] = (sm.Sb[f1 * P + b1] - sm.Sb[b2 * P + b1]) +
+            ex.Efx[(long long)t * D + i] = (sm.Cb[f1 * P + b1] - sm.Cb[b2 * P + b1]) +
                                            (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] - sm.mv[i] + theta;
             double* row = ex.Edf + (long long)t * D * D + (long long)i * D;
             for (int j = 0; j < D; ++j) row[j] = 0.0;
@@ -117,94 +186,104 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             row[b2] = -sm.mv[b1];
             row[b1] = sm.mv[f1] - sm.mv[b2];
         }
+        __syncthreads();
     }
-
-    // ---- factorisation of c S with the inverse carried along -------------------
-    // Each thread keeps its positions of C = c S (-> unscaled factor) and of
-    // W (-> unit-lower inverse) in registers; per pivot only column j of C and
-    // row j of W go through shared memory.
-    double cv[PER], wv[PER];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        cv[q] = 0.0;
-        wv[q] = 0.0;
-        if (pi[q] >= 0) {
-            cv[q] = c * sm.Sb[pi[q] * P + pk[q]];   // numpy.linalg.cholesky reads the lower triangle
-            wv[q] = (pi[q] == pk[q]) ? 1.0 : 0.0;
-            if (pk[q] == 0) sm.col[0][pi[q]] = cv[q];
-            if (pi[q] == 0) sm.wrow[0][0] = 1.0;
-        }
+    // C = c S on the lower triangle (numpy.linalg.cholesky reads the lower triangle)
+    for (int e = tid; e < D * D; e += NTH) {
+        const int i = e / D, j = e - i * D;
+        if (j <= i) sm.Cb[i * P + j] *= c;
     }
     __syncthreads();
-    for (int j = 0; j < D; ++j) {
-        const int buf = j & 1;
-        const double piv = sm.col[buf][j];
-        if (!(piv > 0.0)) {
-            if (tid == 0) sm.bad = 1;
+
+    // ---- blocked factorisation of c S with the inverse carried along ---------------
+    for (int k = 0; k < NB; ++k) {
+        if (warp == 0) factor_diag(sm, k, lane);
+        __syncthreads();
+        {   // (b) exactly four tiles: panel rows i = k+1..4, then V_kj for j = 0..k-1
+            double c0 = 0.0, c1 = 0.0;
+            if (warp < NB - 1 - k) {
+                const int i = k + 1 + warp;   // L_ik = C_ik T_kk^T
+                TILE_MMA(c0, c1, sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Wb[(8 * k + g) * P + 8 * k + kk]);
+                *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * k + 2 * q]) = make_double2(c0, c1);
+            } else {
+                const int j = warp - (NB - 1 - k);   // V_kj = T_kk R_kj
+                if (j < k) {
+                    TILE_MMA(c0, c1, sm.Wb[(8 * k + g) * P + 8 * k + kk], sm.Wb[(8 * k + kk) * P + 8 * j + g]);
+                    *reinterpret_cast<double2*>(&sm.Wb[(8 * k + g) * P + 8 * j + 2 * q]) = make_double2(c0, c1);
+                }
+            }
         }
-        const double rp = 1.0 / piv;
-        if (tid == 0) sm.dvec[j] = piv;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const int i = pi[q], k = pk[q];
-            if (i > j) {
-                const double li = sm.col[buf][i] * rp;
-                if (k > j) cv[q] = fma(-li, sm.col[buf][k], cv[q]);
-                else       wv[q] = fma(-li, sm.wrow[buf][k], wv[q]);
-                if (k == j + 1) sm.col[buf ^ 1][i] = cv[q];
-                if (i == j + 1) sm.wrow[buf ^ 1][k] = wv[q];
+        __syncthreads();
+        if (k == NB - 1) break;
+        {   // (c) trailing updates, tiles dealt round-robin to the four warps
+            int n = 0;
+            for (int i = k + 1; i < NB; ++i) {
+                for (int j = k + 1; j <= i; ++j, ++n) {
+                    if ((n & 3) != warp) continue;   // C_ij -= L_ik L_jk^T
+                    double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]);
+                    TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Cb[(8 * j + g) * P + 8 * k + kk]);
+                    *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
+                }
+                for (int j = 0; j <= k; ++j, ++n) {
+                    if ((n & 3) != warp) continue;   // R_ij -= L_ik V_kj
+                    double2 cc = *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]);
+                    TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Wb[(8 * k + kk) * P + 8 * j + g]);
+                    *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
+                }
             }
         }
         __syncthreads();
     }
-    if (tid < D) sm.rs[tid] = 1.0 / sqrt(sm.dvec[tid]);
-    for (int e = tid; e < MAT; e += NTH) {
-        sm.Lb[e] = 0.0;
-        sm.Wb[e] = 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        if (pi[q] >= 0) {
-            sm.Lb[pi[q] * P + pk[q]] = cv[q] * sm.rs[pk[q]];   // L[i][k] = C[i][k] / sqrt(D_k)
-            sm.Wb[pi[q] * P + pk[q]] = wv[q] * sm.rs[pi[q]];   // V[i][k] = W[i][k] / sqrt(D_i)
-        }
-    }
-    // A m
-    if (tid < D) {
-        double a = 0.0;
-        for (int k = 0; k < D; ++k) a = fma(sm.Ab[tid * P + k], sm.mv[k], a);
-        sm.Am[tid] = a;
-    }
-    __syncthreads();
 
-    // ---- A L into the S buffer ----------------------------------------------------------
-    const int ti = tid >> 4, tj = tid & 15;
-    const int j2 = (tj + 32 < D) ? tj + 32 : D - 1;
+    // ---- A L in place over A (and A m): warp u owns tile-row u; tile-row 4 is shared ----
     {
-        double acc[5][3];
+        double a_own[NB][2], a_r4[NB][2];
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
+        for (int Kb = 0; Kb < NB; ++Kb)
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) acc[r][cc] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < D; ++k) {
-            double a[5], bb[3];
+            for (int h = 0; h < 2; ++h) {
+                a_own[Kb][h] = sm.Ab[(8 * warp + g) * P + 8 * Kb + 4 * h + q];
+                a_r4[Kb][h] = sm.Ab[(32 + g) * P + 8 * Kb + 4 * h + q];
+            }
+        double y = 0.0, y4 = 0.0;
 #pragma unroll
-            for (int r = 0; r < 5; ++r) a[r] = sm.Ab[(ti + 8 * r) * P + k];
-            bb[0] = sm.Lb[k * P + tj];
-            bb[1] = sm.Lb[k * P + tj + 16];
-            bb[2] = sm.Lb[k * P + j2];
+        for (int Kb = 0; Kb < NB; ++Kb)
 #pragma unroll
-            for (int r = 0; r < 5; ++r)
+            for (int h = 0; h < 2; ++h) {
+                const double mk = sm.mv[8 * Kb + 4 * h + q];
+                y = fma(a_own[Kb][h], mk, y);
+                y4 = fma(a_r4[Kb][h], mk, y4);
+            }
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        y += __shfl_xor_sync(0xffffffffu, y, 2);
+        y4 += __shfl_xor_sync(0xffffffffu, y4, 1);
+        y4 += __shfl_xor_sync(0xffffffffu, y4, 2);
+        if (q == 0) {
+            sm.Am[8 * warp + g] = y;
+            if (warp == 0) sm.Am[32 + g] = y4;
+        }
+        __syncthreads();   // every A fragment is in registers before any tile is overwritten
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(a[r], bb[cc], acc[r][cc]);
+        for (int J = 0; J < NB; ++J) {   // own tile-row
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int Kb = J; Kb < NB; ++Kb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    dmma(c0, c1, a_own[Kb][h], sm.Cb[(8 * Kb + 4 * h + q) * P + 8 * J + g]);
+            *reinterpret_cast<double2*>(&sm.Ab[(8 * warp + g) * P + 8 * J + 2 * q]) = make_double2(c0, c1);
         }
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            sm.Sb[(ti + 8 * r) * P + tj] = acc[r][0];
-            sm.Sb[(ti + 8 * r) * P + tj + 16] = acc[r][1];
-            if (tj + 32 < D) sm.Sb[(ti + 8 * r) * P + tj + 32] = acc[r][2];
+        for (int J = 0; J < NB; ++J) {   // tile-row 4: J = 0,1,2 -> warps 0,1,2; J = 3,4 -> warp 3
+            const int owner = J < 3 ? J : 3;
+            if (owner != warp) continue;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int Kb = J; Kb < NB; ++Kb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    dmma(c0, c1, a_r4[Kb][h], sm.Cb[(8 * Kb + 4 * h + q) * P + 8 * J + g]);
+            *reinterpret_cast<double2*>(&sm.Ab[(32 + g) * P + 8 * J + 2 * q]) = make_double2(c0, c1);
         }
     }
     __syncthreads();
@@ -218,12 +297,12 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         for (int h = 0; h < 2; ++h) {
             const int i = lane + 32 * h;
             if (i < D) {
-                const int q = k * D + i;
-                const int q1 = (q + 1 == TOT) ? 0 : q + 1;
-                const int qm1 = (q == 0) ? TOT - 1 : q - 1;
-                const int qm2 = (q < 2) ? q - 2 + TOT : q - 2;
-                const double f = (chi_at(sm, q1) - chi_at(sm, qm2)) * chi_at(sm, qm1) - chi_at(sm, q) + theta;
-                const double r = f + (sm.Am[i] + sg * sm.Sb[i * P + colj]) - sm.bv[i];
+                const int f = k * D + i;
+                const int f1 = (f + 1 == TOT) ? 0 : f + 1;
+                const int fm1 = (f == 0) ? TOT - 1 : f - 1;
+                const int fm2 = (f < 2) ? f - 2 + TOT : f - 2;
+                const double fx = (chi_at(sm, f1) - chi_at(sm, fm2)) * chi_at(sm, fm1) - chi_at(sm, f) + theta;
+                const double r = fx + (sm.Am[i] + sg * sm.Ab[i * P + colj]) - sm.bv[i];
                 part += sm.isg[i] * (r * r);
             }
         }
@@ -260,34 +339,34 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         s.esde_t[(long long)lp * N + t] = sm.esde;
         if (sm.bad) atomicCAS(&s.status[lp], 0, 1 + t);
     }
-    // ---- dEsde/dS = (c^2/2) V^T diag(d) V -----------------------------------------------
+    // ---- dEsde/dS = (c^2/2) V^T diag(d) V on the lower tiles, mirrored ----------------------
     {
-        double acc[5][3];
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) acc[r][cc] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < D; ++k) {
-            const double dk = sm.dv[k];
-            double a[5], bb[3];
-#pragma unroll
-            for (int r = 0; r < 5; ++r) a[r] = sm.Wb[k * P + ti + 8 * r];
-            bb[0] = dk * sm.Wb[k * P + tj];
-            bb[1] = dk * sm.Wb[k * P + tj + 16];
-            bb[2] = dk * sm.Wb[k * P + j2];
-#pragma unroll
-            for (int r = 0; r < 5; ++r)
-#pragma unroll
-                for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(a[r], bb[cc], acc[r][cc]);
-        }
         const double sc = 0.5 * c * c;
+        // tile rows by cost (5 - I) blocks per tile: warp0: I=2, warp1: I=3, warp2: I=1, warp3: I=0 and 4
+        for (int pass = 0; pass < 2; ++pass) {
+            int I;
+            if (pass == 0) I = (warp == 0) ? 2 : (warp == 1 ? 3 : (warp == 2 ? 1 : 0));
+            else if (warp == 3) I = 4;
+            else break;
+            for (int J = 0; J <= I; ++J) {
+                double c0 = 0.0, c1 = 0.0;
+                for (int Kb = I; Kb < NB; ++Kb)
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            double* row = oEs + (long long)(ti + 8 * r) * D;
-            row[tj] = sc * acc[r][0];
-            row[tj + 16] = sc * acc[r][1];
-            if (tj + 32 < D) row[tj + 32] = sc * acc[r][2];
+                    for (int h = 0; h < 2; ++h) {
+                        const int kr = 8 * Kb + 4 * h + q;
+                        dmma(c0, c1, sm.dv[kr] * sm.Wb[kr * P + 8 * I + g], sm.Wb[kr * P + 8 * J + g]);
+                    }
+                const int r = 8 * I + g, cc = 8 * J + 2 * q;
+                const double v0 = sc * c0, v1 = sc * c1;
+                if (I != J) {
+                    *reinterpret_cast<double2*>(&oEs[(long long)r * D + cc]) = make_double2(v0, v1);
+                    oEs[(long long)cc * D + r] = v0;
+                    oEs[(long long)(cc + 1) * D + r] = v1;
+                } else {   // diagonal tile: keep the lower triangle, mirror it
+                    if (r >= cc) { oEs[(long long)r * D + cc] = v0; oEs[(long long)cc * D + r] = v0; }
+                    if (r >= cc + 1) { oEs[(long long)r * D + cc + 1] = v1; oEs[(long long)(cc + 1) * D + r] = v1; }
+                }
+            }
         }
     }
 }

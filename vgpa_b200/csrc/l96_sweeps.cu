@@ -10,15 +10,17 @@
 //   solver tableaux exactly as src/numerics/{euler,heun,runge_kutta2,runge_kutta4}.py
 //   (including runge_kutta2.py:96, where S stands in for A in the inner stage).
 //
-// CTA = 96 threads:
-//   warps 0-1  "team": an 8 x 8 thread grid, each thread owns a 5 x 5 register tile
-//              (rows ti+8r, cols tj+8c) of every 40 x 40 product; operands are read
-//              from shared memory with conflict-free (pitch 42) broadcast loads and
-//              the products run on the FP64 FMA pipe.
-//   warp 2     "vector warp": the mean / lambda recurrences (40 x 40 mat-vecs), the
-//              dL/db row, and ALL global->shared traffic, issued as 1-D bulk async
-//              copies (TMA unit, UBLKCP) that complete on mbarriers one or two
-//              stages ahead of their use.
+// CTA = 160 threads = 5 warps; warp w owns rows 8w..8w+7 of every matrix AND vector:
+//   * its 8 x 40 tile-row of each 40 x 40 product runs on the FP64 tensor cores
+//     (mma.sync m8n8k4 f64, SASS DMMA): per k-step one A fragment and five B fragments
+//     from shared memory (pitch 44 doubles: conflict-free for both fragment shapes)
+//     feed five DMMAs; accumulators stay in registers;
+//   * the mean / lambda recurrences (40 x 40 mat-vecs) ride in the same k-loop: the A
+//     fragment already in registers times the vector entry, reduced over the four
+//     lanes of a fragment row with two shuffles;
+//   * global->shared traffic is 1-D bulk async copies (TMA unit, SASS UBLKCP), eight
+//     320-byte rows per warp, completing on mbarriers one or two stages ahead of use,
+//     with cp.async.bulk.prefetch.L2 pulling the tiles of the next steps into L2.
 // Symmetry: S and Psi are kept EXACTLY symmetric by forming P + P^T through a
 // shared-memory transpose, so one product per RHS evaluation suffices.
 #include "common.cuh"
@@ -28,13 +30,14 @@ namespace vgpa {
 namespace {
 
 constexpr int D = 40;
-constexpr int P = 42;          // shared-memory row pitch (doubles): 336 B rows, 16 B aligned
+constexpr int P = 44;          // shared-memory row pitch (doubles): 352 B rows, 16 B aligned,
+                               // 2P mod 32 = 24 -> DMMA A/B fragment loads hit 16 distinct banks
 constexpr int MAT = D * P;     // one padded matrix
 constexpr int ROWB = D * 8;    // bytes of one matrix row in HBM
-constexpr int TEAM = 64;
-constexpr int NTH = 96;
+constexpr int NMMA = 5;        // MMA warps = tile rows
+constexpr int NTH = 32 * NMMA;
 
-enum { K_CUR = 0, K_MID = 1, K_NEXT = 2, K_SELF = 3 };
+enum { K_CUR = 0, K_MID = 1, K_NEXT = 2 };
 
 __host__ __device__ constexpr int n_stages(int m) { return m == ODE_EULER ? 1 : (m == ODE_RK4 ? 4 : 2); }
 // which A (b / dE) a stage reads: the current index, the neighbour, their midpoint
@@ -64,78 +67,84 @@ __device__ __forceinline__ double final_step(double dt, double ksum)
     return dt * ksum;
 }
 
-// ---- team product: acc[r][c] = sum_k L(ti+8r, k) * R(k, tj+8c) ----------------
-// LK / RK: 0 = plain buffer, 1 = midpoint 0.5*(buf0 + buf1),
-// LK = 2 : fused left operand isg[i]*L0[i][k] - 2*L1[i][k]   (gradient assembly)
-template <int LK, int RK>
-__device__ __forceinline__ void team_mm(const double* __restrict__ L0, const double* __restrict__ L1,
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores.  Lane l = 4 g + q holds
+// a = A[g][q], b = B[q][g], c0 = C[g][2q], c1 = C[g][2q+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// ---- tile-row product with a fused mat-vec -------------------------------------
+//   acc[J] = sum_k L(irow, k) * R(k, 8J + ...)          (five DMMAs per k-step)
+//   yv     = sum_k Av(irow, k) * v[k]                     (one DFMA per k-step)
+// Operand kinds: 0 = plain buffer, 1 = midpoint 0.5*(buf0 + buf1);
+// LK = 2: fused left operand isg*L0 - 2*L1 (gradient assembly; then Av = L0).
+// VK: which matrix feeds the mat-vec: -1 none, 3 = the (possibly fused) left operand's
+// first buffer kind LK, else the kind of (V0, V1) loaded separately.
+template <int LK, int RK, int VK>
+__device__ __forceinline__ void mma_row(const double* __restrict__ L0, const double* __restrict__ L1,
                                         const double* __restrict__ R0, const double* __restrict__ R1,
-                                        const double* __restrict__ isg, int ti, int tj, double (&acc)[5][5])
+                                        const double* __restrict__ V0, const double* __restrict__ V1,
+                                        const double* __restrict__ v, double isg_row, int irow, int g, int q,
+                                        double (&acc)[5][2], double& yv)
 {
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+    for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
+    double y = 0.0;
+    const int la = irow * P + q;   // A fragment: row irow, col k0+q
+    const int lb = q * P + g;      // B fragment: row k0+q, col 8J+g
+#pragma unroll 5
+    for (int k0 = 0; k0 < D; k0 += 4) {
+        double a, av = 0.0;
+        if (LK == 0) a = L0[la + k0];
+        else if (LK == 1) a = 0.5 * (L0[la + k0] + L1[la + k0]);
+        else {
+            av = L0[la + k0];
+            a = fma(isg_row, av, -2.0 * L1[la + k0]);
+        }
+        if (VK == 3) {
+            if (LK != 2) av = a;
+        } else if (VK == K_CUR) av = V0[la + k0];
+        else if (VK == K_NEXT) av = V1[la + k0];
+        else if (VK == K_MID) av = 0.5 * (V0[la + k0] + V1[la + k0]);
+        if (VK >= 0) y = fma(av, v[k0 + q], y);
+        double b[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) acc[r][c] = 0.0;
-    double sc[5];
-    if (LK == 2) {
-#pragma unroll
-        for (int r = 0; r < 5; ++r) sc[r] = isg[ti + 8 * r];
-    }
-#pragma unroll 4
-    for (int k = 0; k < D; ++k) {
-        double a[5], b[5];
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int o = (ti + 8 * r) * P + k;
-            if (LK == 0) a[r] = L0[o];
-            else if (LK == 1) a[r] = 0.5 * (L0[o] + L1[o]);
-            else a[r] = fma(sc[r], L0[o], -2.0 * L1[o]);
+        for (int J = 0; J < 5; ++J) {
+            const int o = lb + k0 * P + 8 * J;
+            if (RK == 0) b[J] = R0[o];
+            else b[J] = 0.5 * (R0[o] + R1[o]);
         }
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const int o = k * P + tj + 8 * c;
-            if (RK == 0) b[c] = R0[o];
-            else b[c] = 0.5 * (R0[o] + R1[o]);
-        }
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        for (int J = 0; J < 5; ++J) dmma(acc[J][0], acc[J][1], a, b[J]);
     }
-}
-
-__device__ __forceinline__ void tile_to_smem(double* __restrict__ T, int ti, int tj, const double (&acc)[5][5])
-{
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) T[(ti + 8 * r) * P + tj + 8 * c] = acc[r][c];
-}
-
-// one row of  Aop v  for the vector warp
-template <int KIND>
-__device__ __forceinline__ double row_dot(const double* __restrict__ Ac, const double* __restrict__ An, int i,
-                                          const double* __restrict__ v)
-{
-    double s = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < D; ++k) {
-        const int o = i * P + k;
-        const double a = KIND == K_CUR ? Ac[o] : (KIND == K_NEXT ? An[o] : 0.5 * (Ac[o] + An[o]));
-        s = fma(a, v[k], s);
+    if (VK >= 0) {
+        y += __shfl_xor_sync(0xffffffffu, y, 1);
+        y += __shfl_xor_sync(0xffffffffu, y, 2);
     }
-    return s;
-}
-template <int KIND>
-__device__ __forceinline__ double pick(const double* __restrict__ c, const double* __restrict__ n, int i)
-{
-    return KIND == K_CUR ? c[i] : (KIND == K_NEXT ? n[i] : 0.5 * (c[i] + n[i]));
+    yv = y;
 }
 
-// issue the bulk copies of one 40 x 40 matrix (row by row into the padded tile)
-__device__ __forceinline__ void load_matrix(double* dst, const double* src, uint64_t* bar, int lane)
+// accumulator tile-row -> shared memory (each lane: two adjacent doubles per tile)
+__device__ __forceinline__ void row_to_smem(double* __restrict__ T, int irow, int q, const double (&acc)[5][2])
 {
-    for (int i = lane; i < D; i += 32) bulk_g2s(dst + i * P, src + i * D, ROWB, bar);
+#pragma unroll
+    for (int J = 0; J < 5; ++J)
+        *reinterpret_cast<double2*>(&T[irow * P + 8 * J + 2 * q]) = make_double2(acc[J][0], acc[J][1]);
+}
+
+template <int KIND>
+__device__ __forceinline__ double pick(double c, double n)
+{
+    return KIND == K_CUR ? c : (KIND == K_NEXT ? n : 0.5 * (c + n));
+}
+
+// every warp issues the bulk copies of its own 8 rows of a 40 x 40 matrix
+__device__ __forceinline__ void load_rows(double* dst, const double* src, uint64_t* bar, int w, int lane)
+{
+    if (lane < 8) bulk_g2s(dst + (8 * w + lane) * P, src + (8 * w + lane) * D, ROWB, bar);
 }
 
 // ===========================================================================
@@ -154,9 +163,9 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
     constexpr int NS = n_stages(METHOD);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const bool team = tid < TEAM;
-    const int ti = tid >> 3, tj = tid & 7;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int irow = 8 * w + g;
     const int lp = blockIdx.x, p = p0 + lp, N = b.N;
     const double* A = x + (long long)p * xs;
     const double* bo = A + (long long)N * D * D;
@@ -183,13 +192,17 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
         sm.sig[tid] = b.sigma[p * b.sigma_stride + tid];
     }
     __syncthreads();
-    if (!team) {  // prologue loads: A_0, b_0 -> slot 0; A_1, b_1 -> slot 1
-        for (int q = 0; q < 2 && q < N; ++q) {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barA[q], D * ROWB + ROWB);
-            __syncwarp();
-            load_matrix(sm.Ab[q], A + (long long)q * D * D, &sm.barA[q], lane);
-            if (lane == 0) bulk_g2s(sm.bb[q], bo + (long long)q * D, ROWB, &sm.barA[q]);
+    // prologue loads: A_0, b_0 -> slot 0; A_1, b_1 -> slot 1; L2 prefetch of the next two
+    for (int c = 0; c < 2 && c < N; ++c) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&sm.barA[c], D * ROWB + ROWB);
+            bulk_g2s(sm.bb[c], bo + (long long)c * D, ROWB, &sm.barA[c]);
         }
+        load_rows(sm.Ab[c], A + (long long)c * D * D, &sm.barA[c], w, lane);
+    }
+    if (tid == 0) {
+        for (int c = 2; c < 5 && c < N; ++c) bulk_prefetch_l2(A + (long long)c * D * D, D * ROWB);
+        bulk_prefetch_l2(bo, ROWB * (N < 8 ? N : 8));
     }
     uint32_t par[2] = {0u, 0u};
     mbar_wait(&sm.barA[0], par[0]);
@@ -200,8 +213,8 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
         const double* Ac = sm.Ab[cur];
         const double* An = sm.Ab[nxt];
         bool next_ready = false;
-        double ksum[5][5];   // team: sum_s w_s k_s of the covariance tile
-        double kv[2] = {0.0, 0.0};  // vector warp: same for its two rows of the mean
+        double ksum[5][2];   // sum_s w_s k_s of this lane's covariance entries
+        double kv = 0.0;     // same for row irow of the mean (replicated over q)
 #pragma unroll
         for (int sidx = 0; sidx < NS; ++sidx) {
             // the covariance inner stage of RK2 uses S in place of A (runge_kutta2.py:96)
@@ -213,74 +226,68 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                 next_ready = true;
             }
             const double* X = (sidx == 0) ? sm.Sb : sm.Hb;
-            double acc[5][5];
-            if (team) {
-                if (self)                 team_mm<0, 0>(X, nullptr, X, nullptr, nullptr, ti, tj, acc);
-                else if (kind == K_CUR)   team_mm<0, 0>(Ac, nullptr, X, nullptr, nullptr, ti, tj, acc);
-                else if (kind == K_NEXT)  team_mm<0, 0>(An, nullptr, X, nullptr, nullptr, ti, tj, acc);
-                else                      team_mm<1, 0>(Ac, An, X, nullptr, nullptr, ti, tj, acc);
-                tile_to_smem(sm.Tb, ti, tj, acc);
-            } else {
-                // mean stage: k = -Aop v + bop  on rows lane and lane+32
-                const double* v = (sidx == 0) ? sm.mv : sm.vt[(sidx - 1) & 1];
-                double ks[2];
+            const double* vX = (sidx == 0) ? sm.mv : sm.vt[(sidx - 1) & 1];
+            double acc[5][2], yv;
+            if (self)                 mma_row<0, 0, K_CUR>(X, nullptr, X, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
+            else if (kind == K_CUR)   mma_row<0, 0, 3>(Ac, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
+            else if (kind == K_NEXT)  mma_row<0, 0, 3>(An, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
+            else                      mma_row<1, 0, 3>(Ac, An, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
+            row_to_smem(sm.Tb, irow, q, acc);
+            {   // mean stage for row irow: k = -Aop v + bop
+                const double bc = sm.bb[cur][irow], bn = sm.bb[nxt][irow];
+                const double bv = kind == K_CUR ? bc : (kind == K_NEXT ? bn : 0.5 * (bc + bn));
+                const double ks = -yv + bv;
+                const double wt = ksum_w(METHOD, sidx);
+                if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
+                if (sidx < NS - 1 && q == 0) sm.vt[sidx & 1][irow] = sm.mv[irow] + (next_coef(METHOD, sidx) * dt) * ks;
+            }
+            __syncthreads();  // T complete / next mean operand visible
+            {
+                const int i = irow;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = lane + 32 * q;
-                    if (i < D) {
-                        double av, bv;
-                        if (kind == K_CUR)       { av = row_dot<K_CUR>(Ac, An, i, v);  bv = pick<K_CUR>(sm.bb[cur], sm.bb[nxt], i); }
-                        else if (kind == K_NEXT) { av = row_dot<K_NEXT>(Ac, An, i, v); bv = pick<K_NEXT>(sm.bb[cur], sm.bb[nxt], i); }
-                        else                     { av = row_dot<K_MID>(Ac, An, i, v);  bv = pick<K_MID>(sm.bb[cur], sm.bb[nxt], i); }
-                        ks[q] = -av + bv;
-                        const double w = ksum_w(METHOD, sidx);
-                        if (w != 0.0) kv[q] = (sidx == 0 || (METHOD == ODE_RK2)) ? w * ks[q] : kv[q] + w * ks[q];
-                        if (sidx < NS - 1)
-                            sm.vt[sidx & 1][i] = sm.mv[i] + (next_coef(METHOD, sidx) * dt) * ks[q];
+                for (int J = 0; J < 5; ++J) {
+                    const int j0 = 8 * J + 2 * q;
+                    const double2 sv = *reinterpret_cast<const double2*>(&sm.Sb[i * P + j0]);
+                    double out[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = j0 + e;
+                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[j * P + i]);
+                        const double wt = ksum_w(METHOD, sidx);
+                        if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
+                        const double sold = e == 0 ? sv.x : sv.y;
+                        if (sidx < NS - 1) out[e] = sold + (next_coef(METHOD, sidx) * dt) * kk;
+                        else out[e] = sold + final_step<METHOD>(dt, ksum[J][e]);
+                    }
+                    if (sidx < NS - 1) {
+                        *reinterpret_cast<double2*>(&sm.Hb[i * P + j0]) = make_double2(out[0], out[1]);
+                    } else {
+                        *reinterpret_cast<double2*>(&sm.Sb[i * P + j0]) = make_double2(out[0], out[1]);
+                        *reinterpret_cast<double2*>(&st[(long long)(k + 1) * D * D + i * D + j0]) =
+                            make_double2(out[0], out[1]);
                     }
                 }
-            }
-            __syncthreads();  // T complete (team) / next mean operand visible
-            if (team) {
-#pragma unroll
-                for (int r = 0; r < 5; ++r)
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        const int i = ti + 8 * r, j = tj + 8 * c;
-                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[r][c] + sm.Tb[j * P + i]);
-                        const double w = ksum_w(METHOD, sidx);
-                        if (w != 0.0) ksum[r][c] = (sidx == 0 || (METHOD == ODE_RK2)) ? w * kk : ksum[r][c] + w * kk;
-                        if (sidx < NS - 1) {
-                            sm.Hb[i * P + j] = sm.Sb[i * P + j] + (next_coef(METHOD, sidx) * dt) * kk;
-                        } else {
-                            const double sn = sm.Sb[i * P + j] + final_step<METHOD>(dt, ksum[r][c]);
-                            sm.Sb[i * P + j] = sn;
-                            st[(long long)(k + 1) * D * D + i * D + j] = sn;
-                        }
-                    }
-            } else if (sidx == NS - 1) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = lane + 32 * q;
-                    if (i < D) {
-                        const double mn = sm.mv[i] + final_step<METHOD>(dt, kv[q]);
-                        sm.mv[i] = mn;
-                        mt[(long long)(k + 1) * D + i] = mn;
-                    }
+                if (sidx == NS - 1 && q == 0) {
+                    const double mn = sm.mv[i] + final_step<METHOD>(dt, kv);
+                    sm.mv[i] = mn;
+                    mt[(long long)(k + 1) * D + i] = mn;
                 }
             }
-            __syncthreads();  // next operand (Hb / Sb) visible; T reusable
+            __syncthreads();  // next operand (Hb / Sb, mv) visible; T reusable
         }
         if (!next_ready && k + 1 < N) {  // Euler: A_{k+1} becomes "current" next step
             mbar_wait(&sm.barA[nxt], par[nxt]);
             par[nxt] ^= 1u;
         }
-        // slot `cur` is dead: prefetch A_{k+2}, b_{k+2} into it
-        if (!team && k + 2 < N) {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB + ROWB);
-            __syncwarp();
-            load_matrix(sm.Ab[cur], A + (long long)(k + 2) * D * D, &sm.barA[cur], lane);
-            if (lane == 0) bulk_g2s(sm.bb[cur], bo + (long long)(k + 2) * D, ROWB, &sm.barA[cur]);
+        // slot `cur` is dead: fetch A_{k+2}, b_{k+2} into it; pull A_{k+5} into L2
+        if (k + 2 < N) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB + ROWB);
+                bulk_g2s(sm.bb[cur], bo + (long long)(k + 2) * D, ROWB, &sm.barA[cur]);
+                if (k + 5 < N) bulk_prefetch_l2(A + (long long)(k + 5) * D * D, D * ROWB);
+                if ((k & 7) == 0 && k + 8 < N) bulk_prefetch_l2(bo + (long long)(k + 8) * D, ROWB * (N - k - 8 < 8 ? N - k - 8 : 8));
+            }
+            load_rows(sm.Ab[cur], A + (long long)(k + 2) * D * D, &sm.barA[cur], w, lane);
         }
     }
 }
@@ -289,9 +296,9 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 // backward sweep + gradient assembly
 // ===========================================================================
 struct BwdSmem {
-    double Pb[MAT], Hb[MAT], Tb[MAT], Ab[2][MAT], Gb[MAT], Sb[MAT];
-    double gv[2][D], mv[D], bv[D], lam[D], lt[2][D], u[D], isg[D], Rv[D], jmv[D];
-    uint64_t barA[2], barS, barG;
+    double Pb[MAT], Hb[MAT], Tb[MAT], Ab[2][MAT], Sb[MAT];
+    double mv[D], bv[D], lam[D], lt[2][D], isg[D], Rv[D];
+    uint64_t barA[2], barS;
 };
 
 struct BwdArgs {
@@ -313,9 +320,9 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     constexpr int NS = n_stages(METHOD);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const bool team = tid < TEAM;
-    const int ti = tid >> 3, tj = tid & 7;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int irow = 8 * w + g;   // the matrix / vector row of this lane
     const int lp = blockIdx.x, p = p0 + lp, N = b.N;
     const double* A = a.A + (long long)lp * a.xs;
     const double* bo = a.bo ? a.bo + (long long)lp * a.xs : nullptr;
@@ -336,7 +343,6 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         mbar_init(&sm.barA[0], 1);
         mbar_init(&sm.barA[1], 1);
         mbar_init(&sm.barS, 1);
-        mbar_init(&sm.barG, 1);
         mbar_fence_init();
     }
     for (int e = tid; e < MAT; e += NTH) sm.Pb[e] = 0.0;  // Psi[N-1] = 0
@@ -344,43 +350,45 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         sm.lam[tid] = 0.0;                                  // lam[N-1] = 0
         sm.isg[tid] = (b.sigma != nullptr) ? 1.0 / b.sigma[p * b.sigma_stride + tid] : 0.0;
         sm.Rv[tid] = (b.R != nullptr) ? b.R[p * b.R_stride + tid] : 1.0;
-        sm.gv[(N - 1) & 1][tid] = dEm[(long long)(N - 1) * D + tid];
     }
-    // dE/dS tile of the current index lives in registers
-    double Greg[5][5];
-    if (team) {
+    // dE/dS (accumulator layout) and dE/dm (row irow) of the current index live in
+    // registers; the neighbour index is prefetched into registers a step ahead
+    double Gc[5][2], Gn[5][2];
+    double gcv, gnv = 0.0;
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-            for (int c = 0; c < 5; ++c)
-                Greg[r][c] = dEs[(long long)(N - 1) * D * D + (ti + 8 * r) * D + tj + 8 * c];
+    for (int J = 0; J < 5; ++J) {
+        const double2 v = *reinterpret_cast<const double2*>(&dEs[(long long)(N - 1) * D * D + irow * D + 8 * J + 2 * q]);
+        Gc[J][0] = v.x;
+        Gc[J][1] = v.y;
+        Gn[J][0] = Gn[J][1] = 0.0;
     }
+    gcv = dEm[(long long)(N - 1) * D + irow];
     __syncthreads();
-    if (!team) {
+    {
         const int t = N - 1;
-        if (lane == 0) mbar_arrive_expect_tx(&sm.barA[t & 1], D * ROWB);
-        __syncwarp();
-        load_matrix(sm.Ab[t & 1], A + (long long)t * D * D, &sm.barA[t & 1], lane);
+        if (tid == 0) mbar_arrive_expect_tx(&sm.barA[t & 1], D * ROWB);
+        load_rows(sm.Ab[t & 1], A + (long long)t * D * D, &sm.barA[t & 1], w, lane);
         if (t >= 1) {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barA[(t - 1) & 1], D * ROWB);
-            __syncwarp();
-            load_matrix(sm.Ab[(t - 1) & 1], A + (long long)(t - 1) * D * D, &sm.barA[(t - 1) & 1], lane);
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barG, D * ROWB + ROWB);
-            __syncwarp();
-            load_matrix(sm.Gb, dEs + (long long)(t - 1) * D * D, &sm.barG, lane);
-            if (lane == 0) bulk_g2s(sm.gv[(t - 1) & 1], dEm + (long long)(t - 1) * D, ROWB, &sm.barG);
+            if (tid == 0) mbar_arrive_expect_tx(&sm.barA[(t - 1) & 1], D * ROWB);
+            load_rows(sm.Ab[(t - 1) & 1], A + (long long)(t - 1) * D * D, &sm.barA[(t - 1) & 1], w, lane);
         }
         if (with_grad) {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barS, D * ROWB + 2 * ROWB);
-            __syncwarp();
-            load_matrix(sm.Sb, st + (long long)t * D * D, &sm.barS, lane);
-            if (lane == 0) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&sm.barS, D * ROWB + 2 * ROWB);
                 bulk_g2s(sm.mv, mt + (long long)t * D, ROWB, &sm.barS);
                 bulk_g2s(sm.bv, bo + (long long)t * D, ROWB, &sm.barS);
             }
+            load_rows(sm.Sb, st + (long long)t * D * D, &sm.barS, w, lane);
+        }
+        if (tid == 0) {
+            for (int c = 2; c < 5 && t - c >= 0; ++c) bulk_prefetch_l2(A + (long long)(t - c) * D * D, D * ROWB);
+            for (int c = 1; c < 4 && t - c >= 0; ++c) {
+                bulk_prefetch_l2(dEs + (long long)(t - c) * D * D, D * ROWB);
+                if (with_grad) bulk_prefetch_l2(st + (long long)(t - c) * D * D, D * ROWB);
+            }
         }
     }
-    uint32_t parA[2] = {0u, 0u}, parS = 0u, parG = 0u;
+    uint32_t parA[2] = {0u, 0u}, parS = 0u;
     mbar_wait(&sm.barA[(N - 1) & 1], parA[(N - 1) & 1]);
     parA[(N - 1) & 1] ^= 1u;
 
@@ -389,172 +397,162 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         const double* Ac = sm.Ab[cur];
         const double* An = sm.Ab[nxt];
         if (keep) {  // lam[t], Psi[t] for vgpa_eval_full / the stand-alone sweep
-            if (team) {
 #pragma unroll
-                for (int r = 0; r < 5; ++r)
+            for (int J = 0; J < 5; ++J)
+                *reinterpret_cast<double2*>(&a.psi_out[(long long)t * D * D + irow * D + 8 * J + 2 * q]) =
+                    *reinterpret_cast<const double2*>(&sm.Pb[irow * P + 8 * J + 2 * q]);
+            if (q == 0) a.lam_out[(long long)t * D + irow] = sm.lam[irow];
+        }
+        // register prefetch of dE/dS[t-1], dE/dm[t-1] (consumed one or two stages later)
+        if (t >= 1) {
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        const int i = ti + 8 * r, j = tj + 8 * c;
-                        a.psi_out[(long long)t * D * D + i * D + j] = sm.Pb[i * P + j];
-                    }
-            } else {
-                for (int i = lane; i < D; i += 32) a.lam_out[(long long)t * D + i] = sm.lam[i];
+            for (int J = 0; J < 5; ++J) {
+                const double2 v = *reinterpret_cast<const double2*>(&dEs[(long long)(t - 1) * D * D + irow * D + 8 * J + 2 * q]);
+                Gn[J][0] = v.x;
+                Gn[J][1] = v.y;
+            }
+            gnv = dEm[(long long)(t - 1) * D + irow];
+            if (tid == 0) {
+                if (t >= 5) bulk_prefetch_l2(A + (long long)(t - 5) * D * D, D * ROWB);
+                if (t >= 4) {
+                    bulk_prefetch_l2(dEs + (long long)(t - 4) * D * D, D * ROWB);
+                    if (with_grad) bulk_prefetch_l2(st + (long long)(t - 4) * D * D, D * ROWB);
+                }
             }
         }
         // ---- gradient at index t (variational.py:263-288) ----------------------
         if (with_grad) {
             mbar_wait(&sm.barS, parS);
             parS ^= 1u;
-            double acc[5][5];
-            if (team) {
-                // W = (Sigma^-1 A_t - 2 Psi_t) S_t
-                team_mm<2, 0>(Ac, sm.Pb, sm.Sb, nullptr, sm.isg, ti, tj, acc);
-            } else {
-                for (int i = lane; i < D; i += 32) {
-                    const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
-                    // <f> of Lorenz 96 (lorenz_96.py:440-462)
-                    const double Ef = (sm.Sb[f1 * P + b1] - sm.Sb[b2 * P + b1]) +
-                                      (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] - sm.mv[i] + theta;
-                    const double am = row_dot<K_CUR>(Ac, An, i, sm.mv);
-                    const double db = sm.isg[i] * (-Ef - am + sm.bv[i]);  // variational.py:324-334
-                    const double ui = db + sm.lam[i];
-                    sm.u[i] = ui;
-                    gb[(long long)t * D + i] = dtm * ui;                   // :280,285
-                }
-            }
-            __syncthreads();
-            if (team) {
+            double acc[5][2], am;
+            // W = (Sigma^-1 A_t - 2 Psi_t) S_t   and   am = (A_t m_t)[irow]
+            mma_row<2, 0, 3>(Ac, sm.Pb, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, acc, am);
+            const int i = irow;
+            const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
+            // <f> of Lorenz 96 (lorenz_96.py:440-462)
+            const double Ef = (sm.Sb[f1 * P + b1] - sm.Sb[b2 * P + b1]) + (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] -
+                              sm.mv[i] + theta;
+            const double is = sm.isg[i];
+            const double db = is * (-Ef - am + sm.bv[i]);      // variational.py:324-334
+            const double ui = db + sm.lam[i];
+            if (q == 0) gb[(long long)t * D + i] = dtm * ui;  // :280,285
+            // row i of <df/dx> S  (Jacobian of lorenz_96.py:34-83 applied to S)
+            const double cb1 = sm.mv[f1] - sm.mv[b2], cf = sm.mv[b1];
 #pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    const int i = ti + 8 * r;
-                    const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
-                    // row i of <df/dx> S  (Jacobian of lorenz_96.py:34-83 applied to S)
-                    const double cb1 = sm.mv[f1] - sm.mv[b2], cf = sm.mv[b1];
-                    const double ui = sm.u[i], is = sm.isg[i];
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        const int j = tj + 8 * c;
-                        const double es = -sm.Sb[i * P + j] + cf * sm.Sb[f1 * P + j] - cf * sm.Sb[b2 * P + j] +
-                                          cb1 * sm.Sb[b1 * P + j];
-                        gA[(long long)t * D * D + i * D + j] = dtm * (acc[r][c] + is * es - ui * sm.mv[j]);
-                    }
-                }
+            for (int J = 0; J < 5; ++J) {
+                const int j0 = 8 * J + 2 * q;
+                const double2 s0 = *reinterpret_cast<const double2*>(&sm.Sb[i * P + j0]);
+                const double2 s1 = *reinterpret_cast<const double2*>(&sm.Sb[f1 * P + j0]);
+                const double2 s2 = *reinterpret_cast<const double2*>(&sm.Sb[b2 * P + j0]);
+                const double2 s3 = *reinterpret_cast<const double2*>(&sm.Sb[b1 * P + j0]);
+                const double2 mj = *reinterpret_cast<const double2*>(&sm.mv[j0]);
+                const double e0 = -s0.x + cf * s1.x - cf * s2.x + cb1 * s3.x;
+                const double e1 = -s0.y + cf * s1.y - cf * s2.y + cb1 * s3.y;
+                *reinterpret_cast<double2*>(&gA[(long long)t * D * D + i * D + j0]) =
+                    make_double2(dtm * (acc[J][0] + is * e0 - ui * mj.x), dtm * (acc[J][1] + is * e1 - ui * mj.y));
             }
         }
         if (t == 0) break;
         // ---- one backward step t -> t-1 ------------------------------------------
         bool next_ready = false;
-        double ksum[5][5];
-        double kv[2] = {0.0, 0.0};
+        double ksum[5][2];
+        double kv = 0.0;
 #pragma unroll
         for (int sidx = 0; sidx < NS; ++sidx) {
             const int kind = stage_kind(METHOD, sidx);
             if (kind != K_CUR && !next_ready) {
                 mbar_wait(&sm.barA[nxt], parA[nxt]);
                 parA[nxt] ^= 1u;
-                mbar_wait(&sm.barG, parG);
-                parG ^= 1u;
                 next_ready = true;
             }
             const double* X = (sidx == 0) ? sm.Pb : sm.Hb;
-            double acc[5][5];
-            if (team) {
-                // Q = X Aop
-                if (kind == K_CUR)       team_mm<0, 0>(X, nullptr, Ac, nullptr, nullptr, ti, tj, acc);
-                else if (kind == K_NEXT) team_mm<0, 0>(X, nullptr, An, nullptr, nullptr, ti, tj, acc);
-                else                     team_mm<0, 1>(X, nullptr, Ac, An, nullptr, ti, tj, acc);
-                tile_to_smem(sm.Tb, ti, tj, acc);
-            } else {
-                const double* v = (sidx == 0) ? sm.lam : sm.lt[(sidx - 1) & 1];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = lane + 32 * q;
-                    if (i < D) {
-                        double av, gk;
-                        if (kind == K_CUR)       { av = row_dot<K_CUR>(Ac, An, i, v);  gk = pick<K_CUR>(sm.gv[cur], sm.gv[nxt], i); }
-                        else if (kind == K_NEXT) { av = row_dot<K_NEXT>(Ac, An, i, v); gk = pick<K_NEXT>(sm.gv[cur], sm.gv[nxt], i); }
-                        else                     { av = row_dot<K_MID>(Ac, An, i, v);  gk = pick<K_MID>(sm.gv[nxt], sm.gv[cur], i); }
-                        const double ks = -gk + av;  // ode_solver.py:77
-                        const double w = ksum_w(METHOD, sidx);
-                        if (w != 0.0) kv[q] = (sidx == 0 || (METHOD == ODE_RK2)) ? w * ks : kv[q] + w * ks;
-                        if (sidx < NS - 1) sm.lt[sidx & 1][i] = sm.lam[i] - (next_coef(METHOD, sidx) * dt) * ks;
-                    }
-                }
+            const double* vX = (sidx == 0) ? sm.lam : sm.lt[(sidx - 1) & 1];
+            double acc[5][2], yv;
+            // Q = X Aop   and   yv = (Aop lam_op)[irow]
+            if (kind == K_CUR)       mma_row<0, 0, K_CUR>(X, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
+            else if (kind == K_NEXT) mma_row<0, 0, K_NEXT>(X, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
+            else                     mma_row<0, 1, K_MID>(X, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, acc, yv);
+            row_to_smem(sm.Tb, irow, q, acc);
+            {
+                const double gk = kind == K_CUR ? gcv : (kind == K_NEXT ? gnv : 0.5 * (gnv + gcv));
+                const double ks = -gk + yv;  // ode_solver.py:77
+                const double wt = ksum_w(METHOD, sidx);
+                if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
+                if (sidx < NS - 1 && q == 0) sm.lt[sidx & 1][irow] = sm.lam[irow] - (next_coef(METHOD, sidx) * dt) * ks;
             }
             __syncthreads();  // T complete
-            if (!team && sidx == 0 && with_grad) {
-                // S_t, m_t, b_t are dead (gradient written): prefetch index t-1
-                if (lane == 0) mbar_arrive_expect_tx(&sm.barS, D * ROWB + 2 * ROWB);
-                __syncwarp();
-                load_matrix(sm.Sb, st + (long long)(t - 1) * D * D, &sm.barS, lane);
-                if (lane == 0) {
+            if (sidx == 0 && with_grad) {
+                // S_t, m_t, b_t are dead (gradient written by every warp): fetch index t-1
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&sm.barS, D * ROWB + 2 * ROWB);
                     bulk_g2s(sm.mv, mt + (long long)(t - 1) * D, ROWB, &sm.barS);
                     bulk_g2s(sm.bv, bo + (long long)(t - 1) * D, ROWB, &sm.barS);
                 }
+                load_rows(sm.Sb, st + (long long)(t - 1) * D * D, &sm.barS, w, lane);
             }
-            if (team) {
+            {
+                const int i = irow;
 #pragma unroll
-                for (int r = 0; r < 5; ++r)
+                for (int J = 0; J < 5; ++J) {
+                    const int j0 = 8 * J + 2 * q;
+                    const double2 pv = *reinterpret_cast<const double2*>(&sm.Pb[i * P + j0]);
+                    double out[2];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        const int i = ti + 8 * r, j = tj + 8 * c;
-                        double g;
-                        if (kind == K_CUR) g = Greg[r][c];
-                        else if (kind == K_NEXT) g = sm.Gb[i * P + j];
-                        else g = 0.5 * (sm.Gb[i * P + j] + Greg[r][c]);
-                        const double kk = -g + (acc[r][c] + sm.Tb[j * P + i]);  // ode_solver.py:94
-                        const double w = ksum_w(METHOD, sidx);
-                        if (w != 0.0) ksum[r][c] = (sidx == 0 || (METHOD == ODE_RK2)) ? w * kk : ksum[r][c] + w * kk;
-                        if (sidx < NS - 1) sm.Hb[i * P + j] = sm.Pb[i * P + j] - (next_coef(METHOD, sidx) * dt) * kk;
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = j0 + e;
+                        double gg;
+                        if (kind == K_CUR) gg = Gc[J][e];
+                        else if (kind == K_NEXT) gg = Gn[J][e];
+                        else gg = 0.5 * (Gn[J][e] + Gc[J][e]);
+                        const double kk = -gg + (acc[J][e] + sm.Tb[j * P + i]);  // ode_solver.py:94
+                        const double wt = ksum_w(METHOD, sidx);
+                        if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
+                        out[e] = (e == 0 ? pv.x : pv.y) - (next_coef(METHOD, sidx) * dt) * kk;
                     }
+                    if (sidx < NS - 1) *reinterpret_cast<double2*>(&sm.Hb[i * P + j0]) = make_double2(out[0], out[1]);
+                }
             }
             if (sidx < NS - 1) __syncthreads();  // Hb visible, T reusable
         }
         if (!next_ready) {  // Euler: index t-1 data becomes "current" next step
             mbar_wait(&sm.barA[nxt], parA[nxt]);
             parA[nxt] ^= 1u;
-            mbar_wait(&sm.barG, parG);
-            parG ^= 1u;
         }
         // ---- final combination + jump at index t-1 -----------------------------------
         const int n_obs = dense ? -1 : b.obs_index[t - 1];
-        if (team) {
+        {
+            const int i = irow;
 #pragma unroll
-            for (int r = 0; r < 5; ++r)
+            for (int J = 0; J < 5; ++J) {
+                const int j0 = 8 * J + 2 * q;
+                const double2 pv = *reinterpret_cast<const double2*>(&sm.Pb[i * P + j0]);
+                double out[2];
 #pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const int i = ti + 8 * r, j = tj + 8 * c;
-                    double pn = sm.Pb[i * P + j] - final_step<METHOD>(dt, ksum[r][c]);
+                for (int e = 0; e < 2; ++e) {
+                    const int j = j0 + e;
+                    double pn = (e == 0 ? pv.x : pv.y) - final_step<METHOD>(dt, ksum[J][e]);
                     if (dense) pn += a.js_dense[(long long)(t - 1) * D * D + i * D + j];
                     else if (n_obs >= 0 && i == j) pn += 0.5 / sm.Rv[i];  // gaussian_like.py:238
-                    sm.Pb[i * P + j] = pn;
-                    Greg[r][c] = sm.Gb[i * P + j];  // dE/dS[t-1] becomes current
+                    out[e] = pn;
+                    Gc[J][e] = Gn[J][e];  // dE/dS[t-1] becomes current
                 }
-        } else {
-            if (!dense && n_obs >= 0 && with_grad) mbar_wait(&sm.barS, parS);  // m[t-1] landed (parity unchanged)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int i = lane + 32 * q;
-                if (i < D) {
-                    double ln = sm.lam[i] - final_step<METHOD>(dt, kv[q]);
-                    if (dense) ln += a.jm_dense[(long long)(t - 1) * D + i];
-                    else if (n_obs >= 0) {
-                        const double mprev = with_grad ? sm.mv[i] : mt[(long long)(t - 1) * D + i];
-                        ln += -(oy[(long long)n_obs * D + i] - mprev) / sm.Rv[i];  // :235
-                    }
-                    sm.lam[i] = ln;
-                }
+                *reinterpret_cast<double2*>(&sm.Pb[i * P + j0]) = make_double2(out[0], out[1]);
             }
+            double ln = sm.lam[i] - final_step<METHOD>(dt, kv);
+            if (dense) ln += a.jm_dense[(long long)(t - 1) * D + i];
+            else if (n_obs >= 0) {
+                if (with_grad) mbar_wait(&sm.barS, parS);  // m[t-1] landed (parity unchanged)
+                const double mprev = with_grad ? sm.mv[i] : mt[(long long)(t - 1) * D + i];
+                ln += -(oy[(long long)n_obs * D + i] - mprev) / sm.Rv[i];  // :235
+            }
+            __syncwarp();
+            if (q == 0) sm.lam[i] = ln;
+            gcv = gnv;
         }
-        __syncthreads();  // Psi, lam of index t-1 complete; slot `cur`, Gb, gv[cur] dead
-        if (!team && t >= 2) {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB);
-            __syncwarp();
-            load_matrix(sm.Ab[cur], A + (long long)(t - 2) * D * D, &sm.barA[cur], lane);
-            if (lane == 0) mbar_arrive_expect_tx(&sm.barG, D * ROWB + ROWB);
-            __syncwarp();
-            load_matrix(sm.Gb, dEs + (long long)(t - 2) * D * D, &sm.barG, lane);
-            if (lane == 0) bulk_g2s(sm.gv[cur], dEm + (long long)(t - 2) * D, ROWB, &sm.barG);
+        __syncthreads();  // Psi, lam of index t-1 complete; slot `cur` dead
+        if (t >= 2) {
+            if (tid == 0) mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB);
+            load_rows(sm.Ab[cur], A + (long long)(t - 2) * D * D, &sm.barA[cur], w, lane);
         }
     }
 }

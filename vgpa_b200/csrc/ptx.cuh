@@ -51,6 +51,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// pull a contiguous global range into L2 ahead of its use (no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // shared -> global bulk copy (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
 {
