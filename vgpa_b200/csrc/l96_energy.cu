@@ -38,7 +38,7 @@ constexpr int P = 44;               // pitch (doubles): DMMA fragment loads conf
 constexpr int MAT = D * P;
 constexpr int ROWB = D * 8;
 constexpr int K = 2 * D + 1;        // sigma points
-constexpr int TOT = K * D;          // flattened sigma-point matrix
+
 constexpr int NTH = 128;
 constexpr int NB = 5;               // 8 x 8 tile grid
 
@@ -60,15 +60,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-// sigma point matrix entry at flattened index f (row k = f / D, column i = f % D)
-__device__ __forceinline__ double chi_at(const EnSmem& sm, int f)
+// L[i][col] with the upper triangle read as zero (upper tiles of Cb hold stale data)
+__device__ __forceinline__ double l_at(const EnSmem& sm, int i, int col)
 {
-    const int k = f / D, i = f - k * D;
-    const double m = sm.mv[i];
-    if (k == 0) return m;
-    const int col = (k <= D) ? k - 1 : k - 1 - D;
-    const double l = (col <= i) ? sm.Cb[i * P + col] : 0.0;   // L is lower triangular
-    return (k <= D) ? m + l : m - l;
+    const double v = sm.Cb[i * P + col];
+    return (col <= i) ? v : 0.0;
 }
 
 // ---- (a) diagonal 8 x 8 block: C_kk -> L_kk (into Cb) and T_kk = L_kk^-1 (into Wb) ----
@@ -288,27 +284,36 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     }
     __syncthreads();
 
-    // ---- residual energies of the 81 sigma points (one warp per sigma point) ----
-    for (int k = warp; k < K; k += NTH / 32) {
-        const int colj = (k == 0) ? 0 : ((k <= D) ? k - 1 : k - 1 - D);
+    // ---- residual energies of the 81 sigma points: ONE THREAD PER SIGMA POINT walks the 40
+    //      state entries with a sliding window (x[i-2], x[i-1], x[i], x[i+1]); lanes of a
+    //      warp read consecutive columns of L and A L (conflict-free), the per-entry
+    //      constants are warp-uniform broadcasts, and no cross-lane reduction is needed ----
+    if (tid < K) {
+        const int k = tid;
+        const int kp = (k == 0) ? K - 1 : k - 1, kn = (k == K - 1) ? 0 : k + 1;
+        const int col = (k == 0) ? 0 : ((k <= D) ? k - 1 : k - 1 - D);
+        const int colp = (kp == 0) ? 0 : ((kp <= D) ? kp - 1 : kp - 1 - D);
+        const int coln = (kn == 0) ? 0 : ((kn <= D) ? kn - 1 : kn - 1 - D);
         const double sg = (k == 0) ? 0.0 : ((k <= D) ? 1.0 : -1.0);
-        double part = 0.0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = lane + 32 * h;
-            if (i < D) {
-                const int f = k * D + i;
-                const int f1 = (f + 1 == TOT) ? 0 : f + 1;
-                const int fm1 = (f == 0) ? TOT - 1 : f - 1;
-                const int fm2 = (f < 2) ? f - 2 + TOT : f - 2;
-                const double fx = (chi_at(sm, f1) - chi_at(sm, fm2)) * chi_at(sm, fm1) - chi_at(sm, f) + theta;
-                const double r = fx + (sm.Am[i] + sg * sm.Ab[i * P + colj]) - sm.bv[i];
-                part += sm.isg[i] * (r * r);
-            }
+        const double sgp = (kp == 0) ? 0.0 : ((kp <= D) ? 1.0 : -1.0);
+        const double sgn = (kn == 0) ? 0.0 : ((kn <= D) ? 1.0 : -1.0);
+        // the flattened roll (lorenz_96.py:27-32) wraps into the neighbouring sigma points
+        double xm2 = sm.mv[D - 2] + sgp * l_at(sm, D - 2, colp);
+        double xm1 = sm.mv[D - 1] + sgp * l_at(sm, D - 1, colp);
+        double x0 = sm.mv[0] + sg * l_at(sm, 0, col);
+        const double xwrap = sm.mv[0] + sgn * l_at(sm, 0, coln);
+        double var = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < D; ++i) {
+            const double xp1 = (i + 1 < D) ? sm.mv[i + 1] + sg * l_at(sm, i + 1, col) : xwrap;
+            const double fx = (xp1 - xm2) * xm1 - x0 + theta;          // lorenz_96.py:85-101
+            const double r = fx + ((sm.Am[i] - sm.bv[i]) + sg * sm.Ab[i * P + col]);
+            var = fma(sm.isg[i], r * r, var);
+            xm2 = xm1;
+            xm1 = x0;
+            x0 = xp1;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) sm.var[k] = part;
+        sm.var[k] = var;
     }
     __syncthreads();
     if (warp == 0) {
