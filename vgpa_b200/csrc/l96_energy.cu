@@ -130,7 +130,7 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int k, int lane)
         }                                                     \
     } while (0)
 
-__global__ void __launch_bounds__(NTH)
+__global__ void __launch_bounds__(NTH, 5)
 l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count, Extra ex)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,7 +166,14 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         }
     }
     if (tid < D) sm.isg[tid] = 1.0 / b.sigma[p * b.sigma_stride + tid];
-    for (int e = tid; e < MAT; e += NTH) sm.Wb[e] = 0.0;
+    // R starts as the identity: only its lower tiles are ever read (diagonal tiles are
+    // written whole by factor_diag), so only the strictly-lower tiles need zeroing
+    for (int e = tid; e < 10 * 32; e += NTH) {
+        const int tile = e >> 5, r8 = (e >> 2) & 7, c2 = (e & 3) * 2;
+        int ti = 1, rem = tile;            // tile -> (ti, tj), ti > tj
+        while (rem >= ti) { rem -= ti; ++ti; }
+        *reinterpret_cast<double2*>(&sm.Wb[(8 * ti + r8) * P + 8 * rem + c2]) = make_double2(0.0, 0.0);
+    }
     mbar_wait(&sm.bar, 0u);
 
     // <f>, <df/dx> for vgpa_eval_full (lorenz_96.py:34-83,440-462); S is still intact
@@ -184,17 +191,14 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         }
         __syncthreads();
     }
-    // C = c S on the lower triangle (numpy.linalg.cholesky reads the lower triangle)
-    for (int e = tid; e < D * D; e += NTH) {
-        const int i = e / D, j = e - i * D;
-        if (j <= i) sm.Cb[i * P + j] *= c;
-    }
+    // The factorisation runs on S itself: chol(c S) = sqrt(c) chol(S), so with L = chol(S),
+    // V = L^-1 the sigma points are m +- sqrt(c) L[:, j] and the scale factors below
+    // become sqrt(c)/2 and c/2 (numpy.linalg.cholesky reads the lower triangle; so do we).
+    const double sqc = sqrt(c);
+    // ---- blocked factorisation of S with the inverse carried along -----------------
+    if (warp == 0) factor_diag(sm, 0, lane);
     __syncthreads();
-
-    // ---- blocked factorisation of c S with the inverse carried along ---------------
     for (int k = 0; k < NB; ++k) {
-        if (warp == 0) factor_diag(sm, k, lane);
-        __syncthreads();
         {   // (b) exactly four tiles: panel rows i = k+1..4, then V_kj for j = 0..k-1
             double c0 = 0.0, c1 = 0.0;
             if (warp < NB - 1 - k) {
@@ -211,17 +215,27 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         }
         __syncthreads();
         if (k == NB - 1) break;
-        {   // (c) trailing updates, tiles dealt round-robin to the four warps
+        // (c) trailing updates with look-ahead: warp 0 updates the next diagonal tile and
+        //     factors it at once, while warps 1-3 share all the other tiles
+        if (warp == 0) {
+            const int i = k + 1;
+            double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * i + 2 * q]);
+            TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Cb[(8 * i + g) * P + 8 * k + kk]);
+            *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * i + 2 * q]) = cc;
+            __syncwarp();
+            factor_diag(sm, k + 1, lane);
+        } else {
             int n = 0;
             for (int i = k + 1; i < NB; ++i) {
-                for (int j = k + 1; j <= i; ++j, ++n) {
-                    if ((n & 3) != warp) continue;   // C_ij -= L_ik L_jk^T
+                for (int j = k + 1; j <= i; ++j) {
+                    if (i == k + 1) continue;          // the look-ahead tile
+                    if ((n++ % 3) != warp - 1) continue;   // C_ij -= L_ik L_jk^T
                     double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]);
                     TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Cb[(8 * j + g) * P + 8 * k + kk]);
                     *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
                 }
-                for (int j = 0; j <= k; ++j, ++n) {
-                    if ((n & 3) != warp) continue;   // R_ij -= L_ik V_kj
+                for (int j = 0; j <= k; ++j) {
+                    if ((n++ % 3) != warp - 1) continue;   // R_ij -= L_ik V_kj
                     double2 cc = *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]);
                     TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Wb[(8 * k + kk) * P + 8 * j + g]);
                     *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
@@ -294,9 +308,9 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         const int col = (k == 0) ? 0 : ((k <= D) ? k - 1 : k - 1 - D);
         const int colp = (kp == 0) ? 0 : ((kp <= D) ? kp - 1 : kp - 1 - D);
         const int coln = (kn == 0) ? 0 : ((kn <= D) ? kn - 1 : kn - 1 - D);
-        const double sg = (k == 0) ? 0.0 : ((k <= D) ? 1.0 : -1.0);
-        const double sgp = (kp == 0) ? 0.0 : ((kp <= D) ? 1.0 : -1.0);
-        const double sgn = (kn == 0) ? 0.0 : ((kn <= D) ? 1.0 : -1.0);
+        const double sg = (k == 0) ? 0.0 : ((k <= D) ? sqc : -sqc);     // +- sqrt(c): L is chol(S)
+        const double sgp = (kp == 0) ? 0.0 : ((kp <= D) ? sqc : -sqc);
+        const double sgn = (kn == 0) ? 0.0 : ((kn <= D) ? sqc : -sqc);
         // the flattened roll (lorenz_96.py:27-32) wraps into the neighbouring sigma points
         double xm2 = sm.mv[D - 2] + sgp * l_at(sm, D - 2, colp);
         double xm1 = sm.mv[D - 1] + sgp * l_at(sm, D - 1, colp);
@@ -332,21 +346,21 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     }
     __syncthreads();
 
-    // ---- dEsde/dm = (c/2) V^T q ------------------------------------------------------------
+    // ---- dEsde/dm = (c/2) Vc^T q = (sqrt(c)/2) V^T q  (Vc = V / sqrt(c)) ---------------------
     double* oEm = s.dEm + ((long long)lp * N + t) * D;
     double* oEs = s.dEs + ((long long)lp * N + t) * D * D;
     if (tid < D) {
         double a = 0.0;
         for (int k = tid; k < D; ++k) a = fma(sm.Wb[k * P + tid], sm.qv[k], a);
-        oEm[tid] = 0.5 * c * a;
+        oEm[tid] = 0.5 * sqc * a;
     }
     if (tid == 0) {
         s.esde_t[(long long)lp * N + t] = sm.esde;
         if (sm.bad) atomicCAS(&s.status[lp], 0, 1 + t);
     }
-    // ---- dEsde/dS = (c^2/2) V^T diag(d) V on the lower tiles, mirrored ----------------------
+    // ---- dEsde/dS = (c^2/2) Vc^T diag(d) Vc = (c/2) V^T diag(d) V, lower tiles, mirrored ------
     {
-        const double sc = 0.5 * c * c;
+        const double sc = 0.5 * c;
         // tile rows by cost (5 - I) blocks per tile: warp0: I=2, warp1: I=3, warp2: I=1, warp3: I=0 and 4
         for (int pass = 0; pass < 2; ++pass) {
             int I;
