@@ -264,12 +264,12 @@ int vgpa_create(const vgpa_desc* d, vgpa_handle** out)
     const long long per = 8LL * N * (2LL * D + 2LL * D * D + 1);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    long long budget = d->scratch_bytes > 0 ? d->scratch_bytes : std::min<long long>(16LL << 30, (long long)(free_b * 0.35));
+    long long budget = d->scratch_bytes > 0 ? d->scratch_bytes : std::min<long long>(24LL << 30, (long long)(free_b * 0.35));
     long long chunk = std::max<long long>(1, std::min<long long>(B, budget / per));
     if (!small_model(d->model) && chunk >= 148) {
         // whole waves: 3 forward CTAs / 2 backward CTAs fit per SM -> multiples of 6 * 148
         const long long wave = 148 * 6;
-        if (chunk >= wave) chunk = (chunk / wave) * wave;
+        if (chunk >= wave) chunk = wave;
         else chunk = (chunk / 148) * 148;
     }
     h->chunk = (int)chunk;

@@ -23,6 +23,7 @@
 //     with cp.async.bulk.prefetch.L2 pulling the tiles of the next steps into L2.
 // Symmetry: S and Psi are kept EXACTLY symmetric by forming P + P^T through a
 // shared-memory transpose, so one product per RHS evaluation suffices.
+#include <cstdio>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -33,6 +34,8 @@ constexpr int D = 40;
 constexpr int P = 44;          // shared-memory row pitch (doubles): 352 B rows, 16 B aligned,
                                // 2P mod 32 = 24 -> DMMA A/B fragment loads hit 16 distinct banks
 constexpr int MAT = D * P;     // one padded matrix
+constexpr int PT = 42;         // pitch of the transpose-exchange buffer: 4 PT mod 32 = 8 makes the
+                               // transposed reads (rows 2q+e, column 8w+g) conflict-free
 constexpr int ROWB = D * 8;    // bytes of one matrix row in HBM
 constexpr int NMMA = 5;        // MMA warps = tile rows
 constexpr int NTH = 32 * NMMA;
@@ -132,7 +135,7 @@ __device__ __forceinline__ void row_to_smem(double* __restrict__ T, int irow, in
 {
 #pragma unroll
     for (int J = 0; J < 5; ++J)
-        *reinterpret_cast<double2*>(&T[irow * P + 8 * J + 2 * q]) = make_double2(acc[J][0], acc[J][1]);
+        *reinterpret_cast<double2*>(&T[irow * PT + 8 * J + 2 * q]) = make_double2(acc[J][0], acc[J][1]);
 }
 
 template <int KIND>
@@ -208,6 +211,10 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     mbar_wait(&sm.barA[0], par[0]);
     par[0] ^= 1u;
 
+#ifdef VGPA_PHASES
+    long long ph_[4] = {0, 0, 0, 0};
+    const long long cstart_ = clock64();
+#endif
     for (int k = 0; k < N - 1; ++k) {
         const int cur = k & 1, nxt = cur ^ 1;
         const double* Ac = sm.Ab[cur];
@@ -228,6 +235,9 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             const double* X = (sidx == 0) ? sm.Sb : sm.Hb;
             const double* vX = (sidx == 0) ? sm.mv : sm.vt[(sidx - 1) & 1];
             double acc[5][2], yv;
+#ifdef VGPA_PHASES
+            long long c0_ = clock64();
+#endif
             if (self)                 mma_row<0, 0, K_CUR>(X, nullptr, X, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
             else if (kind == K_CUR)   mma_row<0, 0, 3>(Ac, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
             else if (kind == K_NEXT)  mma_row<0, 0, 3>(An, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
@@ -241,7 +251,13 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                 if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
                 if (sidx < NS - 1 && q == 0) sm.vt[sidx & 1][irow] = sm.mv[irow] + (next_coef(METHOD, sidx) * dt) * ks;
             }
+#ifdef VGPA_PHASES
+            long long c1_ = clock64();
+#endif
             __syncthreads();  // T complete / next mean operand visible
+#ifdef VGPA_PHASES
+            long long c2_ = clock64();
+#endif
             {
                 const int i = irow;
 #pragma unroll
@@ -252,7 +268,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int j = j0 + e;
-                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[j * P + i]);
+                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[j * PT + i]);
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
                         const double sold = e == 0 ? sv.x : sv.y;
@@ -273,7 +289,14 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                     mt[(long long)(k + 1) * D + i] = mn;
                 }
             }
+#ifdef VGPA_PHASES
+            long long c3_ = clock64();
+#endif
             __syncthreads();  // next operand (Hb / Sb, mv) visible; T reusable
+#ifdef VGPA_PHASES
+            long long c4_ = clock64();
+            ph_[0] += c1_ - c0_; ph_[1] += c2_ - c1_; ph_[2] += c3_ - c2_; ph_[3] += c4_ - c3_;
+#endif
         }
         if (!next_ready && k + 1 < N) {  // Euler: A_{k+1} becomes "current" next step
             mbar_wait(&sm.barA[nxt], par[nxt]);
@@ -290,6 +313,11 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             load_rows(sm.Ab[cur], A + (long long)(k + 2) * D * D, &sm.barA[cur], w, lane);
         }
     }
+#ifdef VGPA_PHASES
+    if ((blockIdx.x == 0 || blockIdx.x == 200) && lane == 0)
+        printf("fwd cta %d warp %d: total %lld  mma %lld  sync1 %lld  epi %lld  sync2 %lld (cycles, %d steps)\n", blockIdx.x, w,
+               clock64() - cstart_, ph_[0], ph_[1], ph_[2], ph_[3], N - 1);
+#endif
 }
 
 // ===========================================================================
@@ -504,7 +532,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                         if (kind == K_CUR) gg = Gc[J][e];
                         else if (kind == K_NEXT) gg = Gn[J][e];
                         else gg = 0.5 * (Gn[J][e] + Gc[J][e]);
-                        const double kk = -gg + (acc[J][e] + sm.Tb[j * P + i]);  // ode_solver.py:94
+                        const double kk = -gg + (acc[J][e] + sm.Tb[j * PT + i]);  // ode_solver.py:94
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
                         out[e] = (e == 0 ? pv.x : pv.y) - (next_coef(METHOD, sidx) * dt) * kk;
