@@ -323,7 +323,7 @@ def run_b200(args):
                                  f"{args.e2e_steps} steps"}
         if world == 1:
             threads = len(os.sched_getaffinity(0))
-            probs = max(threads, 1) * (2 if threads <= 16 else 1)
+            probs = max(threads, 1) * (12 if threads <= 16 else (6 if threads <= 64 else 3))   # ~10-30 s of CPU work
             rate, el_cpu = cpu_port_rate(threads, probs, fam)
             line["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
                                     "sample": f"{probs} L96 N=1001 problems, one OpenMP thread each, "
