@@ -323,8 +323,16 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 // ===========================================================================
 // backward sweep + gradient assembly
 // ===========================================================================
+// In  Q = X A  the multiplier X (Psi or a stage value of it) is the LEFT operand, so a
+// warp only ever needs its OWN eight rows of X as A fragments.  Psi therefore never
+// touches shared memory: it lives in registers in accumulator layout and is turned
+// into A fragments with two shuffles per k-step (the four lanes of a fragment row
+// hold the eight entries of a tile between them).  Shared memory holds only what
+// other warps must see: the A(t) ring, S(t), the lambda vectors and a double-buffered
+// transpose exchange -- which lets 3 CTAs share an SM and needs one barrier per stage.
 struct BwdSmem {
-    double Pb[MAT], Hb[MAT], Tb[MAT], Ab[2][MAT], Sb[MAT];
+    double Ab[2][MAT], Sb[MAT];
+    double Tb[2][D * PT];
     double mv[D], bv[D], lam[D], lt[2][D], isg[D], Rv[D];
     uint64_t barA[2], barS;
 };
@@ -341,8 +349,60 @@ struct BwdArgs {
     double* lam_out; double* psi_out;        // trajectories out (first problem only) or null
 };
 
+// tile-row product whose LEFT operand comes from registers (accumulator layout Xc):
+//   MODE 0: a = X[irow][k]                  MODE 2: a = isg * A0[irow][k] - 2 X[irow][k]
+// RK: right operand plain (0) or midpoint (1);  VK: matrix of the fused mat-vec
+// (3 = A0 of MODE 2, else K_CUR / K_NEXT / K_MID of (V0, V1)).
+template <int MODE, int RK, int VK>
+__device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double* __restrict__ A0,
+                                         const double* __restrict__ R0, const double* __restrict__ R1,
+                                         const double* __restrict__ V0, const double* __restrict__ V1,
+                                         const double* __restrict__ v, double isg_row, int irow, int g, int q,
+                                         int lane, double (&acc)[5][2], double& yv)
+{
+#pragma unroll
+    for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
+    double y = 0.0;
+    const int la = irow * P + q;
+    const int lb = q * P + g;
+    const int srcb = (lane & ~3) + (q >> 1);
+    const bool odd = (q & 1) != 0;
+#pragma unroll
+    for (int n = 0; n < D / 4; ++n) {
+        const int k0 = 4 * n;
+        // entry (irow, k0 + q) sits in tile n/2 at lane 2*(n&1) + q/2 of this row group, slot q&1
+        const int src = srcb + ((n & 1) << 1);
+        const double x0 = __shfl_sync(0xffffffffu, Xc[n >> 1][0], src);
+        const double x1 = __shfl_sync(0xffffffffu, Xc[n >> 1][1], src);
+        const double xv = odd ? x1 : x0;
+        double a, av = 0.0;
+        if (MODE == 2) {
+            av = A0[la + k0];
+            a = fma(isg_row, av, -2.0 * xv);
+        } else {
+            a = xv;
+        }
+        if (VK == K_CUR) av = V0[la + k0];
+        else if (VK == K_NEXT) av = V1[la + k0];
+        else if (VK == K_MID) av = 0.5 * (V0[la + k0] + V1[la + k0]);
+        y = fma(av, v[k0 + q], y);
+        double b[5];
+#pragma unroll
+        for (int J = 0; J < 5; ++J) {
+            const int o = lb + k0 * P + 8 * J;
+            if (RK == 0) b[J] = R0[o];
+            else b[J] = 0.5 * (R0[o] + R1[o]);
+        }
+#pragma unroll
+        for (int J = 0; J < 5; ++J) dmma(acc[J][0], acc[J][1], a, b[J]);
+    }
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    yv = y;
+}
+
 template <int METHOD>
-__global__ void __launch_bounds__(NTH)
+__global__ void __launch_bounds__(NTH, 3)
 l96_bwd_kernel(Batch b, BwdArgs a, int p0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -373,15 +433,14 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         mbar_init(&sm.barS, 1);
         mbar_fence_init();
     }
-    for (int e = tid; e < MAT; e += NTH) sm.Pb[e] = 0.0;  // Psi[N-1] = 0
     if (tid < D) {
         sm.lam[tid] = 0.0;                                  // lam[N-1] = 0
         sm.isg[tid] = (b.sigma != nullptr) ? 1.0 / b.sigma[p * b.sigma_stride + tid] : 0.0;
         sm.Rv[tid] = (b.R != nullptr) ? b.R[p * b.R_stride + tid] : 1.0;
     }
-    // dE/dS (accumulator layout) and dE/dm (row irow) of the current index live in
+    // Psi (rows 8w..8w+7 in accumulator layout), dE/dS and dE/dm of the current index live in
     // registers; the neighbour index is prefetched into registers a step ahead
-    double Gc[5][2], Gn[5][2];
+    double Pc[5][2], Hc[5][2], Gc[5][2], Gn[5][2];
     double gcv, gnv = 0.0;
 #pragma unroll
     for (int J = 0; J < 5; ++J) {
@@ -389,6 +448,8 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         Gc[J][0] = v.x;
         Gc[J][1] = v.y;
         Gn[J][0] = Gn[J][1] = 0.0;
+        Pc[J][0] = Pc[J][1] = 0.0;                          // Psi[N-1] = 0
+        Hc[J][0] = Hc[J][1] = 0.0;
     }
     gcv = dEm[(long long)(N - 1) * D + irow];
     __syncthreads();
@@ -419,6 +480,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     uint32_t parA[2] = {0u, 0u}, parS = 0u;
     mbar_wait(&sm.barA[(N - 1) & 1], parA[(N - 1) & 1]);
     parA[(N - 1) & 1] ^= 1u;
+    int tsel = 0;   // which transpose buffer the next stage writes
 
     for (int t = N - 1; t >= 0; --t) {
         const int cur = t & 1, nxt = cur ^ 1;
@@ -428,7 +490,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
 #pragma unroll
             for (int J = 0; J < 5; ++J)
                 *reinterpret_cast<double2*>(&a.psi_out[(long long)t * D * D + irow * D + 8 * J + 2 * q]) =
-                    *reinterpret_cast<const double2*>(&sm.Pb[irow * P + 8 * J + 2 * q]);
+                    make_double2(Pc[J][0], Pc[J][1]);
             if (q == 0) a.lam_out[(long long)t * D + irow] = sm.lam[irow];
         }
         // register prefetch of dE/dS[t-1], dE/dm[t-1] (consumed one or two stages later)
@@ -454,7 +516,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             parS ^= 1u;
             double acc[5][2], am;
             // W = (Sigma^-1 A_t - 2 Psi_t) S_t   and   am = (A_t m_t)[irow]
-            mma_row<2, 0, 3>(Ac, sm.Pb, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, acc, am);
+            mma_rowx<2, 0, 3>(Pc, Ac, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, lane, acc, am);
             const int i = irow;
             const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
             // <f> of Lorenz 96 (lorenz_96.py:440-462)
@@ -493,14 +555,21 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 parA[nxt] ^= 1u;
                 next_ready = true;
             }
-            const double* X = (sidx == 0) ? sm.Pb : sm.Hb;
             const double* vX = (sidx == 0) ? sm.lam : sm.lt[(sidx - 1) & 1];
+            double* Tw = sm.Tb[tsel];
+            tsel ^= 1;
             double acc[5][2], yv;
             // Q = X Aop   and   yv = (Aop lam_op)[irow]
-            if (kind == K_CUR)       mma_row<0, 0, K_CUR>(X, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
-            else if (kind == K_NEXT) mma_row<0, 0, K_NEXT>(X, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
-            else                     mma_row<0, 1, K_MID>(X, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, acc, yv);
-            row_to_smem(sm.Tb, irow, q, acc);
+            if (sidx == 0) {
+                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Pc, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Pc, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else                     mma_rowx<0, 1, K_MID>(Pc, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+            } else {
+                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Hc, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Hc, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else                     mma_rowx<0, 1, K_MID>(Hc, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+            }
+            row_to_smem(Tw, irow, q, acc);
             {
                 const double gk = kind == K_CUR ? gcv : (kind == K_NEXT ? gnv : 0.5 * (gnv + gcv));
                 const double ks = -gk + yv;  // ode_solver.py:77
@@ -508,7 +577,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
                 if (sidx < NS - 1 && q == 0) sm.lt[sidx & 1][irow] = sm.lam[irow] - (next_coef(METHOD, sidx) * dt) * ks;
             }
-            __syncthreads();  // T complete
+            __syncthreads();  // the only barrier of the stage: transpose buffer and next lambda operand complete
             if (sidx == 0 && with_grad) {
                 // S_t, m_t, b_t are dead (gradient written by every warp): fetch index t-1
                 if (tid == 0) {
@@ -518,31 +587,36 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 }
                 load_rows(sm.Sb, st + (long long)(t - 1) * D * D, &sm.barS, w, lane);
             }
+            if (sidx == NS - 1 && t >= 2) {
+                // slot `cur` is dead once every warp has finished the last product of the step
+                if (!next_ready) {  // Euler: A_{t-1} has not been waited for yet
+                    mbar_wait(&sm.barA[nxt], parA[nxt]);
+                    parA[nxt] ^= 1u;
+                    next_ready = true;
+                }
+                if (tid == 0) mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB);
+                load_rows(sm.Ab[cur], A + (long long)(t - 2) * D * D, &sm.barA[cur], w, lane);
+            }
             {
                 const int i = irow;
 #pragma unroll
                 for (int J = 0; J < 5; ++J) {
-                    const int j0 = 8 * J + 2 * q;
-                    const double2 pv = *reinterpret_cast<const double2*>(&sm.Pb[i * P + j0]);
-                    double out[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int j = j0 + e;
+                        const int j = 8 * J + 2 * q + e;
                         double gg;
                         if (kind == K_CUR) gg = Gc[J][e];
                         else if (kind == K_NEXT) gg = Gn[J][e];
                         else gg = 0.5 * (Gn[J][e] + Gc[J][e]);
-                        const double kk = -gg + (acc[J][e] + sm.Tb[j * PT + i]);  // ode_solver.py:94
+                        const double kk = -gg + (acc[J][e] + Tw[j * PT + i]);  // ode_solver.py:94
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
-                        out[e] = (e == 0 ? pv.x : pv.y) - (next_coef(METHOD, sidx) * dt) * kk;
+                        if (sidx < NS - 1) Hc[J][e] = Pc[J][e] - (next_coef(METHOD, sidx) * dt) * kk;
                     }
-                    if (sidx < NS - 1) *reinterpret_cast<double2*>(&sm.Hb[i * P + j0]) = make_double2(out[0], out[1]);
                 }
             }
-            if (sidx < NS - 1) __syncthreads();  // Hb visible, T reusable
         }
-        if (!next_ready) {  // Euler: index t-1 data becomes "current" next step
+        if (!next_ready) {  // (t == 1 with Euler) keep the barrier phases in step
             mbar_wait(&sm.barA[nxt], parA[nxt]);
             parA[nxt] ^= 1u;
         }
@@ -552,19 +626,15 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             const int i = irow;
 #pragma unroll
             for (int J = 0; J < 5; ++J) {
-                const int j0 = 8 * J + 2 * q;
-                const double2 pv = *reinterpret_cast<const double2*>(&sm.Pb[i * P + j0]);
-                double out[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int j = j0 + e;
-                    double pn = (e == 0 ? pv.x : pv.y) - final_step<METHOD>(dt, ksum[J][e]);
+                    const int j = 8 * J + 2 * q + e;
+                    double pn = Pc[J][e] - final_step<METHOD>(dt, ksum[J][e]);
                     if (dense) pn += a.js_dense[(long long)(t - 1) * D * D + i * D + j];
                     else if (n_obs >= 0 && i == j) pn += 0.5 / sm.Rv[i];  // gaussian_like.py:238
-                    out[e] = pn;
+                    Pc[J][e] = pn;
                     Gc[J][e] = Gn[J][e];  // dE/dS[t-1] becomes current
                 }
-                *reinterpret_cast<double2*>(&sm.Pb[i * P + j0]) = make_double2(out[0], out[1]);
             }
             double ln = sm.lam[i] - final_step<METHOD>(dt, kv);
             if (dense) ln += a.jm_dense[(long long)(t - 1) * D + i];
@@ -577,11 +647,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             if (q == 0) sm.lam[i] = ln;
             gcv = gnv;
         }
-        __syncthreads();  // Psi, lam of index t-1 complete; slot `cur` dead
-        if (t >= 2) {
-            if (tid == 0) mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB);
-            load_rows(sm.Ab[cur], A + (long long)(t - 2) * D * D, &sm.barA[cur], w, lane);
-        }
+        __syncthreads();  // lam of index t-1 visible to every warp
     }
 }
 
