@@ -6,6 +6,7 @@ sys.path.insert(0, '.')
 from vgpa_b200.engine import BatchEvaluator
 
 def main(B=296, N=1001, method="rk2", steps=3, model="L96"):
+    method = {"OU": "rk4", "DW": "euler"}.get(model, method)
     D = {"L96": 40, "L63": 3, "OU": 1, "DW": 1}[model]
     rng = np.random.default_rng(0)
     M = 80 if model == "L96" else 20

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +50,13 @@ struct vgpa_handle {
     long long n_x = 0;   // N * D * (D + 1)
     DevBuf theta, sigma, R, obs_t, obs_index, obs_y, m0, s0, E0, status;
     DevBuf sc_mt, sc_st, sc_dEm, sc_dEs, sc_esde;
+    // second scratch lane: consecutive chunks run on two internal streams so that the
+    // latency-bound energy kernel of one chunk overlaps the sweeps of the other
+    DevBuf sc2_mt, sc2_st, sc2_dEm, sc2_dEs, sc2_esde;
+    Scratch scratch2{};
+    int lanes = 1;
+    cudaStream_t s_lane[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // host-API staging: two slots of one chunk each
     DevBuf st_x[2], st_g[2], st_F;
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -125,9 +133,9 @@ bool small_model(int model) { return model != VGPA_MODEL_L96; }
 
 // one pass over problems [p0, p0 + count) with device buffers
 void run_chunk(vgpa_handle* h, const double* d_x, long long xs, int want_grad, double* d_F, double* d_grad,
-               long long gs, int p0, int count, const Extra& ex, cudaStream_t st)
+               long long gs, int p0, int count, const Extra& ex, cudaStream_t st, int lane = 0)
 {
-    Scratch sc = h->scratch;
+    Scratch sc = lane ? h->scratch2 : h->scratch;
     sc.status = h->status.as<int>() + p0;
     const Batch& b = h->batch;
     const bool small = small_model(b.model);
@@ -284,6 +292,34 @@ int vgpa_create(const vgpa_desc* d, vgpa_handle** out)
             (e = cudaMemset(h->status.p, 0, sizeof(int) * B)) != cudaSuccess)
             return bail(h->cuda_fail(e, "cudaMalloc(scratch)"));
     }
+    {
+        const char* env = getenv("VGPA_LANES");
+        int want = env ? atoi(env) : 1;   // measured: +1 % only (SMs are resource-saturated), not worth 2x scratch
+        h->lanes = (!small_model(d->model) && B > chunk && want >= 2) ? 2 : 1;
+        if (h->lanes == 2) {
+            cudaError_t e;
+            if ((e = h->sc2_mt.alloc(sizeof(double) * chunk * N * D)) != cudaSuccess ||
+                (e = h->sc2_st.alloc(sizeof(double) * chunk * N * D * D)) != cudaSuccess ||
+                (e = h->sc2_dEm.alloc(sizeof(double) * chunk * N * D)) != cudaSuccess ||
+                (e = h->sc2_dEs.alloc(sizeof(double) * chunk * N * D * D)) != cudaSuccess ||
+                (e = h->sc2_esde.alloc(sizeof(double) * chunk * N)) != cudaSuccess ||
+                (e = cudaStreamCreateWithFlags(&h->s_lane[0], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaStreamCreateWithFlags(&h->s_lane[1], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_join[1], cudaEventDisableTiming)) != cudaSuccess) {
+                cudaGetLastError();
+                h->lanes = 1;   // not enough memory for a second lane: run the chunks back to back
+                for (DevBuf* q : {&h->sc2_mt, &h->sc2_st, &h->sc2_dEm, &h->sc2_dEs, &h->sc2_esde}) q->release();
+            }
+        }
+        h->scratch2.mt = h->sc2_mt.as<double>();
+        h->scratch2.st = h->sc2_st.as<double>();
+        h->scratch2.dEm = h->sc2_dEm.as<double>();
+        h->scratch2.dEs = h->sc2_dEs.as<double>();
+        h->scratch2.esde_t = h->sc2_esde.as<double>();
+        h->scratch2.status = h->status.as<int>();
+    }
     h->scratch.mt = h->sc_mt.as<double>();
     h->scratch.st = h->sc_st.as<double>();
     h->scratch.dEm = h->sc_dEm.as<double>();
@@ -312,7 +348,8 @@ void vgpa_destroy(vgpa_handle* h)
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->theta, &h->sigma, &h->R, &h->obs_t, &h->obs_index, &h->obs_y, &h->m0, &h->s0, &h->E0,
-                      &h->status, &h->sc_mt, &h->sc_st, &h->sc_dEm, &h->sc_dEs, &h->sc_esde, &h->st_x[0],
+                      &h->status, &h->sc_mt, &h->sc_st, &h->sc_dEm, &h->sc_dEs, &h->sc_esde, &h->sc2_mt, &h->sc2_st,
+                      &h->sc2_dEm, &h->sc2_dEs, &h->sc2_esde, &h->st_x[0],
                       &h->st_x[1], &h->st_g[0], &h->st_g[1], &h->st_F})
         b->release();
     for (int q = 0; q < 2; ++q) {
@@ -325,6 +362,11 @@ void vgpa_destroy(vgpa_handle* h)
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
         }
+    for (int q = 0; q < 2; ++q) {
+        if (h->s_lane[q]) cudaStreamDestroy(h->s_lane[q]);
+        if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -346,9 +388,24 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * h->d.B, st), "cudaMemsetAsync(status)");
     Extra ex{};
-    for (int p0 = 0; p0 < h->d.B; p0 += h->chunk) {
-        const int count = std::min(h->chunk, h->d.B - p0);
-        run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, st);
+    if (h->lanes == 2) {
+        CK(cudaEventRecord(h->ev_fork, st), "cudaEventRecord");
+        CK(cudaStreamWaitEvent(h->s_lane[0], h->ev_fork, 0), "cudaStreamWaitEvent");
+        CK(cudaStreamWaitEvent(h->s_lane[1], h->ev_fork, 0), "cudaStreamWaitEvent");
+        int ci = 0;
+        for (int p0 = 0; p0 < h->d.B; p0 += h->chunk, ++ci) {
+            const int count = std::min(h->chunk, h->d.B - p0);
+            run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, h->s_lane[ci & 1], ci & 1);
+        }
+        for (int q = 0; q < 2; ++q) {
+            CK(cudaEventRecord(h->ev_join[q], h->s_lane[q]), "cudaEventRecord");
+            CK(cudaStreamWaitEvent(st, h->ev_join[q], 0), "cudaStreamWaitEvent");
+        }
+    } else {
+        for (int p0 = 0; p0 < h->d.B; p0 += h->chunk) {
+            const int count = std::min(h->chunk, h->d.B - p0);
+            run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, st);
+        }
     }
     CK(cudaGetLastError(), "kernel launch");
     h->last_stream = st;
@@ -757,7 +814,8 @@ int64_t vgpa_chunk_size(const vgpa_handle* h) { return h ? h->chunk : 0; }
 int64_t vgpa_scratch_in_use(const vgpa_handle* h)
 {
     if (!h) return 0;
-    return (int64_t)(h->sc_mt.bytes + h->sc_st.bytes + h->sc_dEm.bytes + h->sc_dEs.bytes + h->sc_esde.bytes);
+    return (int64_t)(h->sc_mt.bytes + h->sc_st.bytes + h->sc_dEm.bytes + h->sc_dEs.bytes + h->sc_esde.bytes +
+                     h->sc2_mt.bytes + h->sc2_st.bytes + h->sc2_dEm.bytes + h->sc2_dEs.bytes + h->sc2_esde.bytes);
 }
 
 }  // extern "C"
