@@ -1,0 +1,135 @@
+"""
+Edge cases of the CUDA path against the oracle (through the C ABI): no observations,
+observations at the ends of the grid (the jump at the last index is never applied,
+SURVEY.md 3.8 item 4), the shortest grids, batches that span several chunks and
+staging slots, the device-pointer entry point, and bitwise reproducibility.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_eval_files, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _load(name):
+    return np.load(str(next(p for p in golden_eval_files() if name in p)))
+
+
+def _problem_and_evaluator(g, obs_t=None, obs_y=None, N=None, B=1, **kw):
+    from oracle import Problem, prior_kl0
+    from vgpa_b200.engine import BatchEvaluator
+    D = int(g["D"])
+    N = int(g["N"]) if N is None else N
+    obs_t = g["obs_t"] if obs_t is None else np.asarray(obs_t, dtype=np.int64)
+    obs_y = g["obs_y"] if obs_y is None else obs_y
+    E0 = float(prior_kl0(g["m0"], g["s0"], g["mu0"], g["tau0"], D == 1))
+    prob = Problem(model=str(g["model"]), method=str(g["method"]), D=D, N=N, dt=float(g["dt"]), theta=g["theta"],
+                   sigma=g["sigma"], R=g["R"], obs_t=obs_t, obs_y=obs_y, m0=g["m0"], s0=g["s0"], E0=E0,
+                   dt_model=float(g["dt"]))
+    ev = BatchEvaluator(str(g["model"]), str(g["method"]), N, float(g["dt"]), g["theta"], g["sigma"], g["R"],
+                        obs_t, obs_y, g["m0"], g["s0"], E0, B=B, dt_model=float(g["dt"]), **kw)
+    return prob, ev
+
+
+def _x_prefix(g, N):
+    """The first N time points of the golden evaluation point."""
+    D, N0 = int(g["D"]), int(g["N"])
+    x = g["x"]
+    return np.concatenate([x[:N0 * D * D].reshape(N0, -1)[:N].ravel(), x[N0 * D * D:].reshape(N0, -1)[:N].ravel()])
+
+
+@pytest.mark.parametrize("name", ["eval_OU_rk4", "eval_L63_rk2", "eval_L96_rk2", "eval_L96_heun"])
+def test_no_observations(oracle, name):
+    g = _load(name)
+    D = int(g["D"])
+    prob, ev = _problem_and_evaluator(g, obs_t=np.zeros(0, dtype=np.int64), obs_y=np.zeros((0, D)))
+    with ev:
+        F, G = ev.eval(g["x"])
+    F_o, g_o = oracle.eval(prob, g["x"])
+    assert abs(F[0] - F_o) <= TOL * abs(F_o) and rel_err(G[0], g_o) < TOL
+
+
+@pytest.mark.parametrize("name", ["eval_DW_heun", "eval_L63_euler", "eval_L96_rk4", "eval_L96_euler"])
+def test_observations_at_both_ends(oracle, name):
+    """obs at index 0 (its jump IS applied by the last backward step) and at index N-1
+    (never applied: lam[N-1] = Psi[N-1] = 0 by construction)."""
+    g = _load(name)
+    D, N = int(g["D"]), int(g["N"])
+    obs_t = np.array([0, N // 2, N - 1])
+    rng = np.random.default_rng(2)
+    obs_y = rng.standard_normal((3, D)) + g["m0"]
+    prob, ev = _problem_and_evaluator(g, obs_t=obs_t, obs_y=obs_y)
+    with ev:
+        out = ev.eval_full(g["x"])
+    ref = oracle.eval(prob, g["x"], full=True)
+    for k in ("F", "Eobs", "grad", "lamt", "psit"):
+        assert rel_err(out[k], ref[k]) < TOL, k
+    assert np.all(out["lamt"][-1] == 0.0) and np.all(out["psit"][-1] == 0.0)
+
+
+@pytest.mark.parametrize("name", ["eval_OU_rk4", "eval_L63_heun", "eval_L96_rk2", "eval_L96_rk4", "eval_L96_euler"])
+@pytest.mark.parametrize("N", [2, 3, 4])
+def test_shortest_grids(oracle, name, N):
+    g = _load(name)
+    D = int(g["D"])
+    obs_t = np.array([1]) if N > 2 else np.zeros(0, dtype=np.int64)
+    obs_y = (g["obs_y"][:1] if N > 2 else np.zeros((0, D)))
+    prob, ev = _problem_and_evaluator(g, obs_t=obs_t, obs_y=obs_y, N=N)
+    x = _x_prefix(g, N)
+    with ev:
+        F, G = ev.eval(x)
+    F_o, g_o = oracle.eval(prob, x)
+    assert abs(F[0] - F_o) <= TOL * abs(F_o) and rel_err(G[0], g_o) < TOL
+
+
+@pytest.mark.parametrize("name", ["eval_L96_rk2", "eval_L63_rk4"])
+def test_many_chunks_equal_one_chunk_bitwise(name):
+    """A scratch budget of a few problems forces many passes and both staging slots;
+    results must be bit-identical to the single-pass evaluation, and run to run."""
+    g = _load(name)
+    B = 11
+    rng = np.random.default_rng(8)
+    X = np.stack([g["x"] * (1.0 + 0.01 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    per_problem = 8 * int(g["N"]) * (2 * int(g["D"]) + 2 * int(g["D"]) ** 2 + 1)
+    _, ev1 = _problem_and_evaluator(g, B=B)
+    _, ev3 = _problem_and_evaluator(g, B=B, scratch_bytes=3 * per_problem + 64)
+    with ev1, ev3:
+        assert ev1.chunk_size == B and ev3.chunk_size == 3
+        F1, G1 = ev1.eval(X)
+        F3, G3 = ev3.eval(X)
+        F1b, G1b = ev1.eval(X)
+    assert np.array_equal(F1, F3) and np.array_equal(G1, G3)
+    assert np.array_equal(F1, F1b) and np.array_equal(G1, G1b)
+
+
+def test_device_pointer_entry_point_matches_host_entry_point():
+    import torch
+    g = _load("eval_L96_rk2")
+    B = 4
+    rng = np.random.default_rng(9)
+    X = np.stack([g["x"] * (1.0 + 0.01 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    _, ev = _problem_and_evaluator(g, B=B)
+    with ev:
+        F_h, G_h = ev.eval(X)
+        Xd = torch.from_numpy(X).cuda()
+        Fd = torch.empty(B, dtype=torch.float64, device="cuda")
+        Gd = torch.empty_like(Xd)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ev.eval_device(Xd.data_ptr(), ev.n_x, Fd.data_ptr(), Gd.data_ptr(), ev.n_x, s.cuda_stream)
+        ev.sync()
+        assert ev.launch_count == 8
+    assert np.array_equal(Fd.cpu().numpy(), F_h) and np.array_equal(Gd.cpu().numpy(), G_h)
+
+
+def test_misaligned_device_buffers_are_rejected():
+    import torch
+    g = _load("eval_L96_rk2")
+    _, ev = _problem_and_evaluator(g)
+    with ev:
+        buf = torch.zeros(ev.n_x + 8, dtype=torch.float64, device="cuda")
+        F = torch.zeros(1, dtype=torch.float64, device="cuda")
+        with pytest.raises(ValueError):
+            ev.eval_device(buf.data_ptr() + 8, ev.n_x, F.data_ptr(), None, None, 0)

@@ -23,7 +23,6 @@
 //     with cp.async.bulk.prefetch.L2 pulling the tiles of the next steps into L2.
 // Symmetry: S and Psi are kept EXACTLY symmetric by forming P + P^T through a
 // shared-memory transpose, so one product per RHS evaluation suffices.
-#include <cstdio>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -211,10 +210,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     mbar_wait(&sm.barA[0], par[0]);
     par[0] ^= 1u;
 
-#ifdef VGPA_PHASES
-    long long ph_[4] = {0, 0, 0, 0};
-    const long long cstart_ = clock64();
-#endif
     for (int k = 0; k < N - 1; ++k) {
         const int cur = k & 1, nxt = cur ^ 1;
         const double* Ac = sm.Ab[cur];
@@ -235,9 +230,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             const double* X = (sidx == 0) ? sm.Sb : sm.Hb;
             const double* vX = (sidx == 0) ? sm.mv : sm.vt[(sidx - 1) & 1];
             double acc[5][2], yv;
-#ifdef VGPA_PHASES
-            long long c0_ = clock64();
-#endif
             if (self)                 mma_row<0, 0, K_CUR>(X, nullptr, X, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
             else if (kind == K_CUR)   mma_row<0, 0, 3>(Ac, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
             else if (kind == K_NEXT)  mma_row<0, 0, 3>(An, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
@@ -251,13 +243,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                 if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
                 if (sidx < NS - 1 && q == 0) sm.vt[sidx & 1][irow] = sm.mv[irow] + (next_coef(METHOD, sidx) * dt) * ks;
             }
-#ifdef VGPA_PHASES
-            long long c1_ = clock64();
-#endif
             __syncthreads();  // T complete / next mean operand visible
-#ifdef VGPA_PHASES
-            long long c2_ = clock64();
-#endif
             {
                 const int i = irow;
 #pragma unroll
@@ -289,14 +275,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                     mt[(long long)(k + 1) * D + i] = mn;
                 }
             }
-#ifdef VGPA_PHASES
-            long long c3_ = clock64();
-#endif
             __syncthreads();  // next operand (Hb / Sb, mv) visible; T reusable
-#ifdef VGPA_PHASES
-            long long c4_ = clock64();
-            ph_[0] += c1_ - c0_; ph_[1] += c2_ - c1_; ph_[2] += c3_ - c2_; ph_[3] += c4_ - c3_;
-#endif
         }
         if (!next_ready && k + 1 < N) {  // Euler: A_{k+1} becomes "current" next step
             mbar_wait(&sm.barA[nxt], par[nxt]);
@@ -313,11 +292,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             load_rows(sm.Ab[cur], A + (long long)(k + 2) * D * D, &sm.barA[cur], w, lane);
         }
     }
-#ifdef VGPA_PHASES
-    if ((blockIdx.x == 0 || blockIdx.x == 200) && lane == 0)
-        printf("fwd cta %d warp %d: total %lld  mma %lld  sync1 %lld  epi %lld  sync2 %lld (cycles, %d steps)\n", blockIdx.x, w,
-               clock64() - cstart_, ph_[0], ph_[1], ph_[2], ph_[3], N - 1);
-#endif
 }
 
 // ===========================================================================
@@ -350,11 +324,12 @@ struct BwdArgs {
 };
 
 // tile-row product whose LEFT operand comes from registers (accumulator layout Xc):
-//   MODE 0: a = X[irow][k]                  MODE 2: a = isg * A0[irow][k] - 2 X[irow][k]
+//   MODE 0: a = X[irow][k]      MODE 2: a = isg * (A0[irow][k] + edf[k]) - 2 X[irow][k]
+//   (edf: this lane's entries of row irow of the sparse Lorenz-96 Jacobian <df/dx>)
 // RK: right operand plain (0) or midpoint (1);  VK: matrix of the fused mat-vec
 // (3 = A0 of MODE 2, else K_CUR / K_NEXT / K_MID of (V0, V1)).
 template <int MODE, int RK, int VK>
-__device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double* __restrict__ A0,
+__device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double (&edf)[D / 4], const double* __restrict__ A0,
                                          const double* __restrict__ R0, const double* __restrict__ R1,
                                          const double* __restrict__ V0, const double* __restrict__ V1,
                                          const double* __restrict__ v, double isg_row, int irow, int g, int q,
@@ -378,7 +353,7 @@ __device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double*
         double a, av = 0.0;
         if (MODE == 2) {
             av = A0[la + k0];
-            a = fma(isg_row, av, -2.0 * xv);
+            a = fma(isg_row, av + edf[n], -2.0 * xv);   // Sigma^-1 (A + <df/dx>) - 2 Psi
         } else {
             a = xv;
         }
@@ -441,6 +416,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     // Psi (rows 8w..8w+7 in accumulator layout), dE/dS and dE/dm of the current index live in
     // registers; the neighbour index is prefetched into registers a step ahead
     double Pc[5][2], Hc[5][2], Gc[5][2], Gn[5][2];
+    const double edf0[D / 4] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // unused by the MODE 0 products
     double gcv, gnv = 0.0;
 #pragma unroll
     for (int J = 0; J < 5; ++J) {
@@ -515,31 +491,34 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             mbar_wait(&sm.barS, parS);
             parS ^= 1u;
             double acc[5][2], am;
-            // W = (Sigma^-1 A_t - 2 Psi_t) S_t   and   am = (A_t m_t)[irow]
-            mma_rowx<2, 0, 3>(Pc, Ac, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, lane, acc, am);
             const int i = irow;
             const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
+            // row i of <df/dx> (Jacobian of the Lorenz-96 drift at the mean, lorenz_96.py:34-83):
+            // J[i][i] = -1, J[i][i+1] = m[i-1], J[i][i-2] = -m[i-1], J[i][i-1] = m[i+1] - m[i-2];
+            // this lane keeps the entries that fall on its fragment columns k = 4n + q
+            double edf[D / 4];
+            {
+                const double cf = sm.mv[b1], cb1 = sm.mv[f1] - sm.mv[b2];
+#pragma unroll
+                for (int n = 0; n < D / 4; ++n) {
+                    const int k = 4 * n + q;
+                    edf[n] = (k == i) ? -1.0 : (k == f1) ? cf : (k == b2) ? -cf : (k == b1) ? cb1 : 0.0;
+                }
+            }
+            // W = (Sigma^-1 (A_t + <df/dx>) - 2 Psi_t) S_t   and   am = (A_t m_t)[irow]
+            mma_rowx<2, 0, 3>(Pc, edf, Ac, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, lane, acc, am);
             // <f> of Lorenz 96 (lorenz_96.py:440-462)
             const double Ef = (sm.Sb[f1 * P + b1] - sm.Sb[b2 * P + b1]) + (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] -
                               sm.mv[i] + theta;
-            const double is = sm.isg[i];
-            const double db = is * (-Ef - am + sm.bv[i]);      // variational.py:324-334
+            const double db = sm.isg[i] * (-Ef - am + sm.bv[i]);   // variational.py:324-334
             const double ui = db + sm.lam[i];
-            if (q == 0) gb[(long long)t * D + i] = dtm * ui;  // :280,285
-            // row i of <df/dx> S  (Jacobian of lorenz_96.py:34-83 applied to S)
-            const double cb1 = sm.mv[f1] - sm.mv[b2], cf = sm.mv[b1];
+            if (q == 0) gb[(long long)t * D + i] = dtm * ui;       // :280,285
 #pragma unroll
             for (int J = 0; J < 5; ++J) {
                 const int j0 = 8 * J + 2 * q;
-                const double2 s0 = *reinterpret_cast<const double2*>(&sm.Sb[i * P + j0]);
-                const double2 s1 = *reinterpret_cast<const double2*>(&sm.Sb[f1 * P + j0]);
-                const double2 s2 = *reinterpret_cast<const double2*>(&sm.Sb[b2 * P + j0]);
-                const double2 s3 = *reinterpret_cast<const double2*>(&sm.Sb[b1 * P + j0]);
                 const double2 mj = *reinterpret_cast<const double2*>(&sm.mv[j0]);
-                const double e0 = -s0.x + cf * s1.x - cf * s2.x + cb1 * s3.x;
-                const double e1 = -s0.y + cf * s1.y - cf * s2.y + cb1 * s3.y;
                 *reinterpret_cast<double2*>(&gA[(long long)t * D * D + i * D + j0]) =
-                    make_double2(dtm * (acc[J][0] + is * e0 - ui * mj.x), dtm * (acc[J][1] + is * e1 - ui * mj.y));
+                    make_double2(dtm * (acc[J][0] - ui * mj.x), dtm * (acc[J][1] - ui * mj.y));
             }
         }
         if (t == 0) break;
@@ -561,13 +540,13 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             double acc[5][2], yv;
             // Q = X Aop   and   yv = (Aop lam_op)[irow]
             if (sidx == 0) {
-                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Pc, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
-                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Pc, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
-                else                     mma_rowx<0, 1, K_MID>(Pc, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Pc, edf0, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Pc, edf0, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else                     mma_rowx<0, 1, K_MID>(Pc, edf0, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
             } else {
-                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Hc, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
-                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Hc, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
-                else                     mma_rowx<0, 1, K_MID>(Hc, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Hc, edf0, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Hc, edf0, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else                     mma_rowx<0, 1, K_MID>(Hc, edf0, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
             }
             row_to_smem(Tw, irow, q, acc);
             {
