@@ -297,7 +297,9 @@ def run_b200(args):
     torch.cuda.empty_cache()
     ev_e = BatchEvaluator("L96", "rk2", N_GRID, DT, [8.0], arr["sigma"][:Be], np.ones(D), fam["obs_t"],
                           arr["obs_y"][:Be], arr["m0"][:Be], fam["s0"], arr["E0"][:Be], B=Be,
-                          dt_model=fam["dt_model"], device=local, scratch_bytes=8 << 30)
+                          dt_model=fam["dt_model"], device=local,
+                          # 64-problem chunks: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap
+                          scratch_bytes=64 * 8 * N_GRID * (2 * D + 2 * D * D + 1) + 1024)
     Fe = np.empty(Be)
     for _ in range(2):
         ev_e.eval(xe.array, True, Fe, ge.array)
@@ -340,7 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--per-gpu", type=int, default=PER_GPU, help="problems per GPU (default 4096)")
-    ap.add_argument("--e2e-problems", type=int, default=256)
+    ap.add_argument("--e2e-problems", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
