@@ -280,6 +280,10 @@ int vgpa_create(const vgpa_desc* d, vgpa_handle** out)
         if (chunk >= wave) chunk = wave;
         else chunk = (chunk / 148) * 148;
     }
+    if (const char* ce = getenv("VGPA_CHUNK")) {   // experiments: explicit problems per pass
+        const long long c = atoll(ce);
+        if (c >= 1) chunk = std::min<long long>(c, B);
+    }
     h->chunk = (int)chunk;
     {
         cudaError_t e;

@@ -18,9 +18,13 @@
 //   * the mean / lambda recurrences (40 x 40 mat-vecs) ride in the same k-loop: the A
 //     fragment already in registers times the vector entry, reduced over the four
 //     lanes of a fragment row with two shuffles;
-//   * global->shared traffic is 1-D bulk async copies (TMA unit, SASS UBLKCP), eight
-//     320-byte rows per warp, completing on mbarriers one or two stages ahead of use,
-//     with cp.async.bulk.prefetch.L2 pulling the tiles of the next steps into L2.
+//   * operands that only their owner warp needs never touch shared memory: A(t) in the
+//     forward sweep (left operand: fragments straight from global memory into registers)
+//     and Psi in the backward sweep (registers, turned into fragments with shuffles);
+//   * what every warp must see -- A(t), S(t) in the backward sweep -- arrives by 1-D bulk
+//     async copies (TMA unit, SASS UBLKCP), eight 320-byte rows per warp, completing on
+//     mbarriers one or two stages ahead of use; cp.async.bulk.prefetch.L2 pulls the tiles
+//     of the next steps into L2.
 // Symmetry: S and Psi are kept EXACTLY symmetric by forming P + P^T through a
 // shared-memory transpose, so one product per RHS evaluation suffices.
 #include "common.cuh"
@@ -152,14 +156,56 @@ __device__ __forceinline__ void load_rows(double* dst, const double* src, uint64
 // ===========================================================================
 // forward sweep
 // ===========================================================================
+// In  P = A S  the drift matrix A is the LEFT operand, so a warp only ever needs its
+// OWN eight rows of A(t) -- as DMMA A fragments and for the mean mat-vec.  A therefore
+// never touches shared memory: each lane loads its ten fragment entries of A(t+1)
+// straight from global memory (eight 32-byte row segments per warp instruction, pulled
+// into L2 a few steps ahead by cp.async.bulk.prefetch.L2) at the top of step t and keeps
+// A(t), A(t+1) in registers.  Shared memory holds only S, the stage operand and the
+// transpose exchange (42 KB), so four CTAs share an SM.
 struct FwdSmem {
-    double Sb[MAT], Hb[MAT], Tb[MAT], Ab[2][MAT];
-    double bb[2][D], mv[D], vt[2][D], sig[D];
-    uint64_t barA[2];
+    double Sb[MAT], Hb[MAT];
+    double Tb[D * PT];
+    double mv[D], vt[2][D], sig[D];
 };
 
+// tile-row product with the left operand in registers (fragment layout):
+//   LK 0: a = A0[n]   LK 1: a = 0.5 (A0[n] + A1[n])   LK 3: a = X[irow][k] from shared (RK2 quirk)
+// the mat-vec always uses the register operand (LK 3: A0).
+template <int LK>
+__device__ __forceinline__ void mma_rowa(const double (&A0)[D / 4], const double (&A1)[D / 4],
+                                         const double* __restrict__ X, const double* __restrict__ v, int irow, int g,
+                                         int q, double (&acc)[5][2], double& yv)
+{
+#pragma unroll
+    for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
+    double y = 0.0;
+    const int la = irow * P + q;
+    const int lb = q * P + g;
+#pragma unroll
+    for (int n = 0; n < D / 4; ++n) {
+        const int k0 = 4 * n;
+        double a, av;
+        if (LK == 0) a = av = A0[n];
+        else if (LK == 1) a = av = 0.5 * (A0[n] + A1[n]);
+        else {
+            a = X[la + k0];
+            av = A0[n];
+        }
+        y = fma(av, v[k0 + q], y);
+        double b[5];
+#pragma unroll
+        for (int J = 0; J < 5; ++J) b[J] = X[lb + k0 * P + 8 * J];
+#pragma unroll
+        for (int J = 0; J < 5; ++J) dmma(acc[J][0], acc[J][1], a, b[J]);
+    }
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    yv = y;
+}
+
 template <int METHOD>
-__global__ void __launch_bounds__(NTH)
+__global__ void __launch_bounds__(NTH, 4)
 l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,11 +221,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     double* st = s.st + (long long)lp * N * D * D;
     const double dt = b.dt;
 
-    if (tid == 0) {
-        mbar_init(&sm.barA[0], 1);
-        mbar_init(&sm.barA[1], 1);
-        mbar_fence_init();
-    }
     // initial state: S0 -> Sb (and trajectory slot 0), m0 -> mv
     for (int e = tid; e < D * D; e += NTH) {
         const int i = e / D, j = e % D;
@@ -193,28 +234,33 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
         mt[tid] = v;
         sm.sig[tid] = b.sigma[p * b.sigma_stride + tid];
     }
-    __syncthreads();
-    // prologue loads: A_0, b_0 -> slot 0; A_1, b_1 -> slot 1; L2 prefetch of the next two
-    for (int c = 0; c < 2 && c < N; ++c) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(&sm.barA[c], D * ROWB + ROWB);
-            bulk_g2s(sm.bb[c], bo + (long long)c * D, ROWB, &sm.barA[c]);
-        }
-        load_rows(sm.Ab[c], A + (long long)c * D * D, &sm.barA[c], w, lane);
-    }
     if (tid == 0) {
-        for (int c = 2; c < 5 && c < N; ++c) bulk_prefetch_l2(A + (long long)c * D * D, D * ROWB);
+        for (int c = 1; c < 5 && c < N; ++c) bulk_prefetch_l2(A + (long long)c * D * D, D * ROWB);
         bulk_prefetch_l2(bo, ROWB * (N < 8 ? N : 8));
     }
-    uint32_t par[2] = {0u, 0u};
-    mbar_wait(&sm.barA[0], par[0]);
-    par[0] ^= 1u;
+    // this lane's fragment entries (row irow, columns 4n + q) of A(k) and A(k+1), and b[irow]
+    double Ac[D / 4], An[D / 4];
+    const double* arow = A + (long long)irow * D + q;
+#pragma unroll
+    for (int n = 0; n < D / 4; ++n) {
+        Ac[n] = arow[4 * n];
+        An[n] = 0.0;
+    }
+    double bc = bo[irow], bn = 0.0;
+    __syncthreads();
 
     for (int k = 0; k < N - 1; ++k) {
-        const int cur = k & 1, nxt = cur ^ 1;
-        const double* Ac = sm.Ab[cur];
-        const double* An = sm.Ab[nxt];
-        bool next_ready = false;
+        // A(k+1), b(k+1) for this step's later stages: loads stay in flight during stage 0
+        {
+            const double* an = arow + (long long)(k + 1) * D * D;
+#pragma unroll
+            for (int n = 0; n < D / 4; ++n) An[n] = an[4 * n];
+            bn = bo[(long long)(k + 1) * D + irow];
+            if (tid == 0) {
+                if (k + 5 < N) bulk_prefetch_l2(A + (long long)(k + 5) * D * D, D * ROWB);
+                if ((k & 7) == 0 && k + 8 < N) bulk_prefetch_l2(bo + (long long)(k + 8) * D, ROWB * (N - k - 8 < 8 ? N - k - 8 : 8));
+            }
+        }
         double ksum[5][2];   // sum_s w_s k_s of this lane's covariance entries
         double kv = 0.0;     // same for row irow of the mean (replicated over q)
 #pragma unroll
@@ -222,21 +268,15 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             // the covariance inner stage of RK2 uses S in place of A (runge_kutta2.py:96)
             const int kind = stage_kind(METHOD, sidx);
             const bool self = (METHOD == ODE_RK2 && sidx == 0);
-            if (kind != K_CUR && !next_ready) {
-                mbar_wait(&sm.barA[nxt], par[nxt]);
-                par[nxt] ^= 1u;
-                next_ready = true;
-            }
             const double* X = (sidx == 0) ? sm.Sb : sm.Hb;
             const double* vX = (sidx == 0) ? sm.mv : sm.vt[(sidx - 1) & 1];
             double acc[5][2], yv;
-            if (self)                 mma_row<0, 0, K_CUR>(X, nullptr, X, nullptr, Ac, An, vX, 0.0, irow, g, q, acc, yv);
-            else if (kind == K_CUR)   mma_row<0, 0, 3>(Ac, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
-            else if (kind == K_NEXT)  mma_row<0, 0, 3>(An, nullptr, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
-            else                      mma_row<1, 0, 3>(Ac, An, X, nullptr, nullptr, nullptr, vX, 0.0, irow, g, q, acc, yv);
+            if (self)                 mma_rowa<3>(Ac, An, X, vX, irow, g, q, acc, yv);
+            else if (kind == K_CUR)   mma_rowa<0>(Ac, An, X, vX, irow, g, q, acc, yv);
+            else if (kind == K_NEXT)  mma_rowa<0>(An, An, X, vX, irow, g, q, acc, yv);
+            else                      mma_rowa<1>(Ac, An, X, vX, irow, g, q, acc, yv);
             row_to_smem(sm.Tb, irow, q, acc);
             {   // mean stage for row irow: k = -Aop v + bop
-                const double bc = sm.bb[cur][irow], bn = sm.bb[nxt][irow];
                 const double bv = kind == K_CUR ? bc : (kind == K_NEXT ? bn : 0.5 * (bc + bn));
                 const double ks = -yv + bv;
                 const double wt = ksum_w(METHOD, sidx);
@@ -277,20 +317,9 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             }
             __syncthreads();  // next operand (Hb / Sb, mv) visible; T reusable
         }
-        if (!next_ready && k + 1 < N) {  // Euler: A_{k+1} becomes "current" next step
-            mbar_wait(&sm.barA[nxt], par[nxt]);
-            par[nxt] ^= 1u;
-        }
-        // slot `cur` is dead: fetch A_{k+2}, b_{k+2} into it; pull A_{k+5} into L2
-        if (k + 2 < N) {
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&sm.barA[cur], D * ROWB + ROWB);
-                bulk_g2s(sm.bb[cur], bo + (long long)(k + 2) * D, ROWB, &sm.barA[cur]);
-                if (k + 5 < N) bulk_prefetch_l2(A + (long long)(k + 5) * D * D, D * ROWB);
-                if ((k & 7) == 0 && k + 8 < N) bulk_prefetch_l2(bo + (long long)(k + 8) * D, ROWB * (N - k - 8 < 8 ? N - k - 8 : 8));
-            }
-            load_rows(sm.Ab[cur], A + (long long)(k + 2) * D * D, &sm.barA[cur], w, lane);
-        }
+#pragma unroll
+        for (int n = 0; n < D / 4; ++n) Ac[n] = An[n];
+        bc = bn;
     }
 }
 
