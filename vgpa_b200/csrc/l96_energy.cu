@@ -49,7 +49,6 @@ struct EnSmem {
     double mv[D], bv[D], Am[D], isg[D], qv[D], dv[D];
     double var[K + 3];
     double esde;
-    uint64_t bar;
     int bad;
 };
 
@@ -147,24 +146,13 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     const double kap = 1.05 * D, c = D + kap;                 // utilities.py:271
     const double w0 = kap / c, wi = 1.0 / (2.0 * c);          // :290-291
 
-    if (tid == 0) {
-        mbar_init(&sm.bar, 1);
-        mbar_fence_init();
-        sm.bad = 0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0) mbar_arrive_expect_tx(&sm.bar, 2 * D * ROWB + 2 * ROWB);
-        __syncwarp();
-        for (int i = lane; i < D; i += 32) {
-            bulk_g2s(sm.Cb + i * P, St + i * D, ROWB, &sm.bar);
-            bulk_g2s(sm.Ab + i * P, At + i * D, ROWB, &sm.bar);
-        }
-        if (lane == 0) {
-            bulk_g2s(sm.mv, mt, ROWB, &sm.bar);
-            bulk_g2s(sm.bv, bt, ROWB, &sm.bar);
-        }
-    }
+    if (tid == 0) sm.bad = 0;
+    // S(t), A(t), m(t), b(t): 16-byte cp.async copies (LDGSTS) spread over the CTA
+    cp_async_matrix(sm.Cb, St, P, tid, NTH);
+    cp_async_matrix(sm.Ab, At, P, tid, NTH);
+    cp_async_vector(sm.mv, mt, tid, 0);
+    cp_async_vector(sm.bv, bt, tid, 32);
+    cp_async_commit();
     if (tid < D) sm.isg[tid] = 1.0 / b.sigma[p * b.sigma_stride + tid];
     // R starts as the identity: only its lower tiles are ever read (diagonal tiles are
     // written whole by factor_diag), so only the strictly-lower tiles need zeroing
@@ -174,7 +162,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         while (rem >= ti) { rem -= ti; ++ti; }
         *reinterpret_cast<double2*>(&sm.Wb[(8 * ti + r8) * P + 8 * rem + c2]) = make_double2(0.0, 0.0);
     }
-    mbar_wait(&sm.bar, 0u);
+    cp_async_wait<0>();
+    __syncthreads();
 
     // <f>, <df/dx> for vgpa_eval_full (lorenz_96.py:34-83,440-462); S is still intact
     if (ex.Efx != nullptr && lp == 0) {

@@ -56,6 +56,31 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+// ---- cp.async (SASS LDGSTS): 16-byte global -> shared copies without register staging ----
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// a 40 x 40 row-major matrix into a padded shared tile (row pitch `pitch` doubles), split over `nth` threads
+__device__ __forceinline__ void cp_async_matrix(double* dst, const double* src, int pitch, int tid, int nth)
+{
+    for (int c = tid; c < 40 * 20; c += nth) {
+        const int i = c / 20, k = c - i * 20;
+        cp_async16(dst + i * pitch + 2 * k, src + i * 40 + 2 * k);
+    }
+}
+// a 40-vector (20 chunks)
+__device__ __forceinline__ void cp_async_vector(double* dst, const double* src, int tid, int first)
+{
+    const int c = tid - first;
+    if (c >= 0 && c < 20) cp_async16(dst + 2 * c, src + 2 * c);
+}
 // shared -> global bulk copy (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
 {
