@@ -20,11 +20,14 @@
 //
 // Blocked algorithm on 8 x 8 tiles (5 x 5 tile grid), bulk work on the FP64 tensor
 // cores (mma.sync m8n8k4 f64, SASS DMMA):
-//   for k = 0..4:  (a) 8 x 8 diagonal block: L_kk, T_kk = L_kk^-1 by one warp, rows in
-//                      registers, pivots exchanged with shuffles (no square roots inside
-//                      the loop: LDL^T, scaled at the end)
-//                  (b) panel L_ik = C_ik T_kk^T (i > k) and V_kj = T_kk R_kj (j < k): 4 tiles
-//                  (c) trailing C_ij -= L_ik L_jk^T and R_ij -= L_ik V_kj
+//   for k = 0..4:  (a) 8 x 8 diagonal block L_kk by one warp, the whole lower triangle in the
+//                      registers of every lane (no shuffles; LDL^T with hardware-seeded
+//                      reciprocals, scaled at the end) -- the serial spine, so latency-tuned
+//                  (b) panel L_ik by per-row triangular solves (i > k)
+//                  (c) trailing C_ij -= L_ik L_jk^T as DMMA tiles, with look-ahead: the next
+//                      diagonal block is factored while the other warps finish (c)
+//   V = L^-1 afterwards: diagonal tiles by per-column solves, then block columns in parallel
+//   (one warp per block column) as DMMA tile products
 //   A L in place over A;  81 residual energies with warp-shuffle reductions;
 //   V^T diag(d) V on the lower tiles, mirrored on store.
 #include "common.cuh"
@@ -47,6 +50,7 @@ struct EnSmem {
     double Wb[MAT];   // R -> V = L^-1 (lower block triangle, zero elsewhere)
     double Ab[MAT];   // A(t) -> A L
     double mv[D], bv[D], Am[D], isg[D], qv[D], dv[D];
+    double dinv[D];   // 1 / L[j][j]
     double var[K + 3];
     double esde;
     int bad;
@@ -66,54 +70,109 @@ __device__ __forceinline__ double l_at(const EnSmem& sm, int i, int col)
     return (col <= i) ? v : 0.0;
 }
 
-// ---- (a) diagonal 8 x 8 block: C_kk -> L_kk (into Cb) and T_kk = L_kk^-1 (into Wb) ----
-// one warp; lane r < 8 owns row r of the block in registers
+// reciprocal and reciprocal square root from the hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits)
+// plus two Newton steps: full double precision without the long IEEE division / sqrt sequences,
+// which sit on the serial critical path of the diagonal-block factorisation
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(fma(-hx * y, y, 0.5), y, y);
+    y = fma(fma(-hx * y, y, 0.5), y, y);
+    return y;
+}
+
+// ---- (a) diagonal 8 x 8 block: C_kk -> L_kk (into Cb), 1/L_jj (into dinv) -------------
+// Latency is everything here (this is the serial spine of the factorisation), so every
+// lane of the warp holds the WHOLE lower triangle (36 values) in registers and runs the
+// LDL^T elimination redundantly: no shuffles, no shared-memory round trips; per pivot
+// the dependent chain is reciprocal -> multiply -> one FMA.
 __device__ __forceinline__ void factor_diag(EnSmem& sm, int k, int lane)
 {
-    const unsigned FULL = 0xffffffffu;
-    const int r = lane & 7;
-    double c[8], wv[8], dd[8];
-    const double* src = &sm.Cb[(8 * k + r) * P + 8 * k];
+    double c[8][8], d[8];
+    const double* src = &sm.Cb[(8 * k) * P + 8 * k];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        c[j] = src[j];
-        wv[j] = (j == r) ? 1.0 : 0.0;
-    }
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) c[i][j] = src[i * P + j];   // warp-uniform (broadcast) loads
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const double pj = __shfl_sync(FULL, c[j], j);   // pivot D_j
+        const double pj = c[j][j];
         bad |= !(pj > 0.0);
-        dd[j] = pj;
-        const double lrj = c[j] * (1.0 / pj);            // unit-lower factor entry (rows r > j)
+        d[j] = pj;
+        const double rp = fast_rcp(pj);
 #pragma unroll
-        for (int kx = j + 1; kx < 8; ++kx) {
-            const double ckj = __shfl_sync(FULL, c[j], kx);   // C[kx][j], unscaled
-            c[kx] = fma(-lrj, ckj, c[kx]);
-        }
+        for (int i = j + 1; i < 8; ++i) {
+            const double lij = c[i][j] * rp;           // unit-lower factor entry
 #pragma unroll
-        for (int kx = 0; kx <= j; ++kx) {
-            const double wjk = __shfl_sync(FULL, wv[kx], j);  // W[j][kx]
-            if (r > j) wv[kx] = fma(-lrj, wjk, wv[kx]);
+            for (int m = j + 1; m <= i; ++m) c[i][m] = fma(-lij, c[m][j], c[i][m]);
         }
     }
     if (bad && lane == 0) sm.bad = 1;
-    // scale: L = Lt D^1/2, T = D^-1/2 Lt^-1
-    double dr = dd[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) dr = (r == j) ? dd[j] : dr;
-    const double my_rs = 1.0 / sqrt(dr);   // one square root per lane, exchanged below
+    // scale: L = Lt D^1/2
     double rs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rs[j] = __shfl_sync(FULL, my_rs, j);
-    if (lane < 8) {
-        double* lo = &sm.Cb[(8 * k + r) * P + 8 * k];
-        double* to = &sm.Wb[(8 * k + r) * P + 8 * k];
+    for (int j = 0; j < 8; ++j) rs[j] = fast_rsqrt(d[j]);
+    if (lane == 0) {
+        double* lo = &sm.Cb[(8 * k) * P + 8 * k];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            lo[j] = (j < r) ? c[j] * rs[j] : (j == r ? dd[j] * rs[j] : 0.0);
-            to[j] = (j <= r) ? wv[j] * rs[r] : 0.0;
-        }
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                lo[i * P + j] = (j < i) ? c[i][j] * rs[j] : (j == i ? d[j] * rs[j] : 0.0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm.dinv[8 * k + j] = rs[j];
+    }
+}
+
+// ---- (b) panel tile: solve X L_kk^T = C_ik; lane r < 8 owns row r of the 8 x 8 tile ----
+__device__ __forceinline__ void panel_solve(EnSmem& sm, int i, int k, int lane)
+{
+    const int r = lane & 7;
+    double x[8];
+    double* row = &sm.Cb[(8 * i + r) * P + 8 * k];
+    const double* Lk = &sm.Cb[(8 * k) * P + 8 * k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = row[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double xj = x[j] * sm.dinv[8 * k + j];
+        x[j] = xj;
+#pragma unroll
+        for (int m = j + 1; m < 8; ++m) x[m] = fma(-xj, Lk[m * P + j], x[m]);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = x[j];
+    }
+}
+
+// ---- T_kk = L_kk^-1 (into the diagonal tile of Wb); lane c < 8 owns column c ------------
+__device__ __forceinline__ void invert_diag(EnSmem& sm, int k, int lane)
+{
+    const int c = lane & 7;
+    const double* Lk = &sm.Cb[(8 * k) * P + 8 * k];
+    double y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < i; ++m) acc = fma(-Lk[i * P + m], y[m], acc);
+        y[i] = acc * sm.dinv[8 * k + i];
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm.Wb[(8 * k + i) * P + 8 * k + c] = y[i];
     }
 }
 
@@ -154,14 +213,6 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     cp_async_vector(sm.bv, bt, tid, 32);
     cp_async_commit();
     if (tid < D) sm.isg[tid] = 1.0 / b.sigma[p * b.sigma_stride + tid];
-    // R starts as the identity: only its lower tiles are ever read (diagonal tiles are
-    // written whole by factor_diag), so only the strictly-lower tiles need zeroing
-    for (int e = tid; e < 10 * 32; e += NTH) {
-        const int tile = e >> 5, r8 = (e >> 2) & 7, c2 = (e & 3) * 2;
-        int ti = 1, rem = tile;            // tile -> (ti, tj), ti > tj
-        while (rem >= ti) { rem -= ti; ++ti; }
-        *reinterpret_cast<double2*>(&sm.Wb[(8 * ti + r8) * P + 8 * rem + c2]) = make_double2(0.0, 0.0);
-    }
     cp_async_wait<0>();
     __syncthreads();
 
@@ -187,25 +238,12 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     // ---- blocked factorisation of S with the inverse carried along -----------------
     if (warp == 0) factor_diag(sm, 0, lane);
     __syncthreads();
-    for (int k = 0; k < NB; ++k) {
-        {   // (b) exactly four tiles: panel rows i = k+1..4, then V_kj for j = 0..k-1
-            double c0 = 0.0, c1 = 0.0;
-            if (warp < NB - 1 - k) {
-                const int i = k + 1 + warp;   // L_ik = C_ik T_kk^T
-                TILE_MMA(c0, c1, sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Wb[(8 * k + g) * P + 8 * k + kk]);
-                *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * k + 2 * q]) = make_double2(c0, c1);
-            } else {
-                const int j = warp - (NB - 1 - k);   // V_kj = T_kk R_kj
-                if (j < k) {
-                    TILE_MMA(c0, c1, sm.Wb[(8 * k + g) * P + 8 * k + kk], sm.Wb[(8 * k + kk) * P + 8 * j + g]);
-                    *reinterpret_cast<double2*>(&sm.Wb[(8 * k + g) * P + 8 * j + 2 * q]) = make_double2(c0, c1);
-                }
-            }
-        }
+    for (int k = 0; k < NB - 1; ++k) {
+        // (b) panel rows i = k+1..4: one tile per warp
+        if (warp < NB - 1 - k) panel_solve(sm, k + 1 + warp, k, lane);
         __syncthreads();
-        if (k == NB - 1) break;
-        // (c) trailing updates with look-ahead: warp 0 updates the next diagonal tile and
-        //     factors it at once, while warps 1-3 share all the other tiles
+        // (c) trailing update C_ij -= L_ik L_jk^T with look-ahead: warp 0 updates the next
+        //     diagonal tile and factors it at once, warps 1-3 share the other tiles
         if (warp == 0) {
             const int i = k + 1;
             double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * i + 2 * q]);
@@ -215,24 +253,39 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             factor_diag(sm, k + 1, lane);
         } else {
             int n = 0;
-            for (int i = k + 1; i < NB; ++i) {
+            for (int i = k + 2; i < NB; ++i)
                 for (int j = k + 1; j <= i; ++j) {
-                    if (i == k + 1) continue;          // the look-ahead tile
-                    if ((n++ % 3) != warp - 1) continue;   // C_ij -= L_ik L_jk^T
+                    if ((n++ % 3) != warp - 1) continue;
                     double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]);
                     TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Cb[(8 * j + g) * P + 8 * k + kk]);
                     *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
                 }
-                for (int j = 0; j <= k; ++j) {
-                    if ((n++ % 3) != warp - 1) continue;   // R_ij -= L_ik V_kj
-                    double2 cc = *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]);
-                    TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * k + kk], sm.Wb[(8 * k + kk) * P + 8 * j + g]);
-                    *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
-                }
-            }
         }
         __syncthreads();
     }
+
+    // ---- V = L^-1, off the factorisation's critical path -------------------------------
+    // diagonal tiles T_kk = L_kk^-1 (independent of each other) ...
+    invert_diag(sm, warp, lane);
+    if (warp == 0) invert_diag(sm, 4, lane);
+    __syncthreads();
+    // ... then block column j by warp j: V_ij = -T_ii sum_{m=j}^{i-1} L_im V_mj, i = j+1..4
+    {
+        const int j = warp;
+        for (int i = j + 1; i < NB; ++i) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int m = j; m < i; ++m)
+                TILE_MMA(s0, s1, sm.Cb[(8 * i + g) * P + 8 * m + kk], sm.Wb[(8 * m + kk) * P + 8 * j + g]);
+            *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]) = make_double2(s0, s1);
+            __syncwarp();
+            double v0 = 0.0, v1 = 0.0;
+            TILE_MMA(v0, v1, -sm.Wb[(8 * i + g) * P + 8 * i + kk], sm.Wb[(8 * i + kk) * P + 8 * j + g]);
+            __syncwarp();
+            *reinterpret_cast<double2*>(&sm.Wb[(8 * i + g) * P + 8 * j + 2 * q]) = make_double2(v0, v1);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
 
     // ---- A L in place over A (and A m): warp u owns tile-row u; tile-row 4 is shared ----
     {
