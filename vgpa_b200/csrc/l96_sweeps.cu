@@ -23,8 +23,9 @@
 //     and Psi in the backward sweep (registers, turned into fragments with shuffles);
 //   * what every warp must see -- A(t), S(t) in the backward sweep -- arrives by 1-D bulk
 //     async copies (TMA unit, SASS UBLKCP), eight 320-byte rows per warp, completing on
-//     mbarriers one or two stages ahead of use; cp.async.bulk.prefetch.L2 pulls the tiles
-//     of the next steps into L2.
+//     mbarriers one or two stages ahead of use.  (Explicit L2 prefetching further ahead
+//     was measured and removed: with 444 CTAs streaming, prefetched lines were evicted
+//     before use and DRAM traffic rose 60 % above the algorithmic bytes.)
 // Symmetry: S and Psi are kept EXACTLY symmetric by forming P + P^T through a
 // shared-memory transpose, so one product per RHS evaluation suffices.
 #include "common.cuh"
@@ -159,9 +160,8 @@ __device__ __forceinline__ void load_rows(double* dst, const double* src, uint64
 // In  P = A S  the drift matrix A is the LEFT operand, so a warp only ever needs its
 // OWN eight rows of A(t) -- as DMMA A fragments and for the mean mat-vec.  A therefore
 // never touches shared memory: each lane loads its ten fragment entries of A(t+1)
-// straight from global memory (eight 32-byte row segments per warp instruction, pulled
-// into L2 a few steps ahead by cp.async.bulk.prefetch.L2) at the top of step t and keeps
-// A(t), A(t+1) in registers.  Shared memory holds only S, the stage operand and the
+// straight from global memory (eight 32-byte row segments per warp instruction) at the
+// top of step t -- a stage before their first use -- and keeps A(t), A(t+1) in registers.  Shared memory holds only S, the stage operand and the
 // transpose exchange (42 KB), so four CTAs share an SM.
 struct FwdSmem {
     double Sb[MAT], Hb[MAT];
@@ -234,10 +234,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
         mt[tid] = v;
         sm.sig[tid] = b.sigma[p * b.sigma_stride + tid];
     }
-    if (tid == 0) {
-        for (int c = 1; c < 5 && c < N; ++c) bulk_prefetch_l2(A + (long long)c * D * D, D * ROWB);
-        bulk_prefetch_l2(bo, ROWB * (N < 8 ? N : 8));
-    }
     // this lane's fragment entries (row irow, columns 4n + q) of A(k) and A(k+1), and b[irow]
     double Ac[D / 4], An[D / 4];
     const double* arow = A + (long long)irow * D + q;
@@ -256,10 +252,6 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 #pragma unroll
             for (int n = 0; n < D / 4; ++n) An[n] = an[4 * n];
             bn = bo[(long long)(k + 1) * D + irow];
-            if (tid == 0) {
-                if (k + 5 < N) bulk_prefetch_l2(A + (long long)(k + 5) * D * D, D * ROWB);
-                if ((k & 7) == 0 && k + 8 < N) bulk_prefetch_l2(bo + (long long)(k + 8) * D, ROWB * (N - k - 8 < 8 ? N - k - 8 : 8));
-            }
         }
         double ksum[5][2];   // sum_s w_s k_s of this lane's covariance entries
         double kv = 0.0;     // same for row irow of the mean (replicated over q)
@@ -474,13 +466,6 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             }
             load_rows(sm.Sb, st + (long long)t * D * D, &sm.barS, w, lane);
         }
-        if (tid == 0) {
-            for (int c = 2; c < 5 && t - c >= 0; ++c) bulk_prefetch_l2(A + (long long)(t - c) * D * D, D * ROWB);
-            for (int c = 1; c < 4 && t - c >= 0; ++c) {
-                bulk_prefetch_l2(dEs + (long long)(t - c) * D * D, D * ROWB);
-                if (with_grad) bulk_prefetch_l2(st + (long long)(t - c) * D * D, D * ROWB);
-            }
-        }
     }
     uint32_t parA[2] = {0u, 0u}, parS = 0u;
     mbar_wait(&sm.barA[(N - 1) & 1], parA[(N - 1) & 1]);
@@ -507,13 +492,6 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 Gn[J][1] = v.y;
             }
             gnv = dEm[(long long)(t - 1) * D + irow];
-            if (tid == 0) {
-                if (t >= 5) bulk_prefetch_l2(A + (long long)(t - 5) * D * D, D * ROWB);
-                if (t >= 4) {
-                    bulk_prefetch_l2(dEs + (long long)(t - 4) * D * D, D * ROWB);
-                    if (with_grad) bulk_prefetch_l2(st + (long long)(t - 4) * D * D, D * ROWB);
-                }
-            }
         }
         // ---- gradient at index t (variational.py:263-288) ----------------------
         if (with_grad) {

@@ -54,7 +54,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // pull a contiguous global range into L2 ahead of its use (no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
 {
+#ifndef VGPA_NO_L2_PREFETCH
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+#endif
 }
 // ---- cp.async (SASS LDGSTS): 16-byte global -> shared copies without register staging ----
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
