@@ -3,6 +3,7 @@
 // average clock64 cycles CTA thread 0 spends in each phase.  Development aid.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I vgpa_b200/csrc -o tools/energy_prof tools/energy_prof.cu
 #define VGPA_EN_PROF
+#include <cstdlib>
 #include "../vgpa_b200/csrc/l96_energy.cu"
 #include <cstdio>
 #include <cstdlib>

@@ -65,8 +65,6 @@ constexpr int K = 2 * D + 1;        // sigma points
 
 constexpr int NTH = 128;
 constexpr int NB = 5;               // 8 x 8 tile grid
-// bytes the bulk copies bring in: lower block triangle of S, all of A, m and b
-constexpr unsigned LOAD_BYTES = 8 * (64 + 128 + 192 + 256 + 320) + D * ROWB + 2 * ROWB;
 
 struct EnSmem {
     double Cb[MAT];   // S (lower block triangle) -> Lt, unit lower factor of S = Lt diag(dd) Lt^T; upper part zero
@@ -79,8 +77,6 @@ struct EnSmem {
     double rp[D];     // 1 / d_j
     double sdv[D];    // sqrt(c d_j): column scale of the sigma points
     double var[K + 3];
-    double esde;
-    uint64_t bar;
     int bad;
 };
 
@@ -89,6 +85,19 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
+}
+
+// named barriers (ids 1..): producer side arrives without blocking, consumer side waits
+// (ids and counts are immediates so that the compiler reserves exactly the barriers used)
+template <int ID>
+__device__ __forceinline__ void bar_sync()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(128) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_arrive()
+{
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(128) : "memory");
 }
 
 // reciprocal and reciprocal square root from the hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits)
@@ -136,6 +145,14 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
     const int cc = lane & 7;
     double y[8];
     bool bad = false;
+    // What this lane will store at the end: chunk (lane & 3) of row (lane >> 2) of Lt, and
+    // d / 1/d of pivot (lane & 7).  Captured with selects as the rows become final, so the spine
+    // has no divergent code and the whole tile leaves in ONE store instruction (a warp-wide store of
+    // identical values costs 4 shared-memory wavefronts, a divergent single-lane store costs the
+    // spine a reconvergence: both were measured).
+    const int lrow = lane >> 2, lch = lane & 3;
+    double2 mine = make_double2(0.0, 0.0);
+    double dmine = 0.0, rmine = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const double pj = c[j][j];
@@ -154,26 +171,35 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
             }
             c[j + 1][j] = l1;
         }
-        sm.dd[8 * kb + j] = pj;
-        sm.rp[8 * kb + j] = rpj;
+        if (cc == j) {
+            dmine = pj;
+            rmine = rpj;
+        }
         // row j of the unit-lower factor is final: entry j of column cc of its inverse ...
         double acc = (j == cc) ? 1.0 : 0.0;
 #pragma unroll
         for (int m = 0; m < j; ++m) acc = fma(-c[j][m], y[m], acc);
         y[j] = acc;
         tinv[j * P + cc] = acc;
-        // ... and row j of Lt with explicit ones / zeros
+        // ... and my chunk of row j of Lt (explicit ones / zeros)
+        {
+            double2 pick = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int m = 0; m < 8; m += 2) {
-            double v[2];
+            for (int ch = 0; ch < 4; ++ch) {
+                double v[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int mm = m + e;
-                v[e] = (mm < j) ? c[j][mm < j ? mm : 0] : (mm == j ? 1.0 : 0.0);
+                for (int e = 0; e < 2; ++e) {
+                    const int mm = 2 * ch + e;
+                    v[e] = (mm < j) ? c[j][mm < j ? mm : 0] : (mm == j ? 1.0 : 0.0);
+                }
+                if (lch == ch) pick = make_double2(v[0], v[1]);
             }
-            *reinterpret_cast<double2*>(&tile[j * P + m]) = make_double2(v[0], v[1]);
+            if (lrow == j) mine = pick;
         }
     }
+    *reinterpret_cast<double2*>(&tile[lrow * P + 2 * lch]) = mine;
+    sm.dd[8 * kb + cc] = dmine;
+    sm.rp[8 * kb + cc] = rmine;
     if (bad) sm.bad = 1;
 }
 
@@ -189,124 +215,141 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
         }                                                     \
     } while (0)
 
-// ---- (b) panel tile (i, KB): Lt_ik = C_ik Tt_kk^T D_k^-1, in place ------------------------
-template <int KB>
-__device__ __forceinline__ void panel_tile(EnSmem& sm, int i, int g, int q)
+// All tile indices below are RUN-TIME values and the block loop of the factorisation is not
+// unrolled: the kernel is executed once per CTA as straight-line code, so its size is what the
+// instruction cache sees (a fully unrolled version, 64 KB, hit the cache only 73 % of the time
+// and starved the serial spine: profiles/README.md).
+// ---- (b) panel tile (i, kb): Lt_ik = C_ik Tt_kk^T D_k^-1, in place ------------------------
+__device__ __forceinline__ void panel_tile(EnSmem& sm, int i, int kb, int g, int q)
 {
     double c0 = 0.0, c1 = 0.0;
-    TILE_MMA(c0, c1, sm.Cb[(8 * i + g) * P + 8 * KB + kk], sm.Wb[(8 * KB + g) * P + 8 * KB + kk]);
-    const double2 r = *reinterpret_cast<const double2*>(&sm.rp[8 * KB + 2 * q]);
+    const double* ca = &sm.Cb[(8 * i + g) * P + 8 * kb];
+    const double* tb = &sm.Wb[(8 * kb + g) * P + 8 * kb];
+    TILE_MMA(c0, c1, ca[kk], tb[kk]);
+    const double2 r = *reinterpret_cast<const double2*>(&sm.rp[8 * kb + 2 * q]);
     // mma.sync consumed every lane's operands: the tile may be overwritten
-    *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * KB + 2 * q]) = make_double2(c0 * r.x, c1 * r.y);
+    *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * kb + 2 * q]) = make_double2(c0 * r.x, c1 * r.y);
 }
 
 // ---- (c) trailing tile (i, j) -= Lt_ik D_k Lt_jk^T ------------------------------------------
-template <int KB>
-__device__ __forceinline__ void trail_tile(EnSmem& sm, int i, int j, int g, int q)
+__device__ __forceinline__ void trail_tile(EnSmem& sm, int i, int j, int kb, int g, int q)
 {
-    double2 cc = *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]);
-    TILE_MMA(cc.x, cc.y, -sm.Cb[(8 * i + g) * P + 8 * KB + kk] * sm.dd[8 * KB + kk],
-             sm.Cb[(8 * j + g) * P + 8 * KB + kk]);
-    *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * j + 2 * q]) = cc;
+    double* ct = &sm.Cb[(8 * i + g) * P + 8 * j + 2 * q];
+    const double* la = &sm.Cb[(8 * i + g) * P + 8 * kb];
+    const double* lb = &sm.Cb[(8 * j + g) * P + 8 * kb];
+    const double* dk = &sm.dd[8 * kb];
+    double2 cc = *reinterpret_cast<double2*>(ct);
+    TILE_MMA(cc.x, cc.y, -la[kk] * dk[kk], lb[kk]);
+    *reinterpret_cast<double2*>(ct) = cc;
 }
 
 // ---- tile (I, J), I > J, of Vt = Lt^-1: Vt_IJ = -Tt_II sum_{m=J}^{I-1} Lt_Im Vt_mJ; block rows
 //      < I of Vt and block columns < I of Lt are final --------------------------------------
-template <int I, int J>
-__device__ __forceinline__ void v_tile(EnSmem& sm, int g, int q)
+__device__ __forceinline__ void v_tile(EnSmem& sm, int I, int J, int g, int q)
 {
-    double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
-#pragma unroll
-    for (int m = J; m < I; ++m) {   // two accumulator pairs: half the dependent DMMA chain
-        if ((m - J) & 1) TILE_MMA(u0, u1, sm.Cb[(8 * I + g) * P + 8 * m + kk], sm.Wb[(8 * m + kk) * P + 8 * J + g]);
-        else             TILE_MMA(s0, s1, sm.Cb[(8 * I + g) * P + 8 * m + kk], sm.Wb[(8 * m + kk) * P + 8 * J + g]);
-    }
-    *reinterpret_cast<double2*>(&sm.Wb[(8 * I + g) * P + 8 * J + 2 * q]) = make_double2(s0 + u0, s1 + u1);
+    double s0 = 0.0, s1 = 0.0;
+    const double* la = &sm.Cb[(8 * I + g) * P];
+    const double* vb = &sm.Wb[8 * J + g];
+#pragma unroll 1
+    for (int m = J; m < I; ++m) TILE_MMA(s0, s1, la[8 * m + kk], vb[(8 * m + kk) * P]);
+    double* out = &sm.Wb[(8 * I + g) * P + 8 * J + 2 * q];
+    *reinterpret_cast<double2*>(out) = make_double2(s0, s1);
     __syncwarp();
     double v0 = 0.0, v1 = 0.0;
-    TILE_MMA(v0, v1, -sm.Wb[(8 * I + g) * P + 8 * I + kk], sm.Wb[(8 * I + kk) * P + 8 * J + g]);
+    const double* ta = &sm.Wb[(8 * I + g) * P + 8 * I];
+    TILE_MMA(v0, v1, -ta[kk], vb[(8 * I + kk) * P]);
     __syncwarp();
-    *reinterpret_cast<double2*>(&sm.Wb[(8 * I + g) * P + 8 * J + 2 * q]) = make_double2(v0, v1);
+    *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
 }
 
-// ---- tile (i, J) of A Lt, in place over A: column J of Lt is final, columns > J of A intact ----
-template <int J>
-__device__ __forceinline__ void al_tile(EnSmem& sm, int i, int g, int q)
+// ---- tiles (i0, J) and (i0 + 1, J) of A Lt (PAIR: i0 + 1 < 5), in place over A: column J of Lt is
+//      final, columns > J of A intact.  The two tile rows share every B fragment.  Column 0 reads
+//      all of A, so cv = A m - b + theta comes with it (WITH_CV). ----------------------------
+template <bool PAIR, bool WITH_CV>
+__device__ __forceinline__ void al_tiles(EnSmem& sm, int i0, int J, double theta, int g, int q)
 {
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-#pragma unroll
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, y0 = 0.0, y1 = 0.0;
+    const double* aa = &sm.Ab[(8 * i0 + g) * P + q];
+    const double* lb = &sm.Cb[q * P + 8 * J + g];
+#pragma unroll 1
     for (int Kb = J; Kb < NB; ++Kb) {
-        dmma(c0, c1, sm.Ab[(8 * i + g) * P + 8 * Kb + q], sm.Cb[(8 * Kb + q) * P + 8 * J + g]);
-        dmma(e0, e1, sm.Ab[(8 * i + g) * P + 8 * Kb + 4 + q], sm.Cb[(8 * Kb + 4 + q) * P + 8 * J + g]);
-    }
-    *reinterpret_cast<double2*>(&sm.Ab[(8 * i + g) * P + 8 * J + 2 * q]) = make_double2(c0 + e0, c1 + e1);
-}
-
-// row I of Vt (tiles J < I), task-distributed
-template <int I, int J0 = 0>
-struct VRow {
-    template <typename F>
-    static __device__ __forceinline__ void run(EnSmem& sm, int g, int q, F&& mine)
-    {
-        if constexpr (J0 < I) {
-            if (mine()) v_tile<I, J0>(sm, g, q);
-            VRow<I, J0 + 1>::run(sm, g, q, mine);
-        }
-    }
-};
-
-// one block step of the factorisation; on entry Lt_kk / Tt_kk / D_k of block KB are in place.
-// While warp 0 runs the serial spine (next diagonal tile + its factorisation), warps 1-3 finish
-// the trailing update and then work in its shadow: block row KB of Vt and block column KB of A Lt
-// (both only need what is final by now).
-template <int KB>
-__device__ __forceinline__ void factor_step(EnSmem& sm, int warp, int lane, int g, int q)
-{
-    // (b) panel rows i = KB+1..4: one tile per warp
-    if (warp < NB - 1 - KB) panel_tile<KB>(sm, KB + 1 + warp, g, q);
-    __syncthreads();
-    if (warp == 0) {
-        trail_tile<KB>(sm, KB + 1, KB + 1, g, q);
-        __syncwarp();
-        factor_diag(sm, KB + 1, lane);
-    } else {
-        int n = 0;
-        auto mine = [&]() { return (n++ % 3) == warp - 1; };
-#pragma unroll
-        for (int i = KB + 2; i < NB; ++i)
-#pragma unroll
-            for (int j = KB + 1; j <= i; ++j)
-                if (mine()) trail_tile<KB>(sm, i, j, g, q);
-        if constexpr (KB >= 1) VRow<KB>::run(sm, g, q, mine);
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (mine()) al_tile<KB>(sm, i, g, q);
-    }
-    __syncthreads();
-}
-
-// ---- tile-row I of dEsde/dS = (c/2) Vt^T diag(dw) Vt (lower tiles J <= I), mirrored on store ----
-template <int I>
-__device__ __forceinline__ void deds_row(const EnSmem& sm, double* __restrict__ oEs, double sc, int g, int q)
-{
-    double a[NB - I][2];
-#pragma unroll
-    for (int Kb = I; Kb < NB; ++Kb)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int kr = 8 * Kb + 4 * h + q;
-            a[Kb - I][h] = sm.cv[kr] * sm.Wb[kr * P + 8 * I + g];
+            const int ko = 8 * Kb + 4 * h;
+            const double bf = lb[ko * P];
+            const double a0 = aa[ko];
+            dmma(c0, c1, a0, bf);
+            double a1 = 0.0;
+            if (PAIR) {
+                a1 = aa[8 * P + ko];
+                dmma(e0, e1, a1, bf);
+            }
+            if (WITH_CV) {
+                const double mk = sm.mv[ko + q];
+                y0 = fma(a0, mk, y0);
+                if (PAIR) y1 = fma(a1, mk, y1);
+            }
         }
+    }
+    *reinterpret_cast<double2*>(&sm.Ab[(8 * i0 + g) * P + 8 * J + 2 * q]) = make_double2(c0, c1);
+    if (PAIR) *reinterpret_cast<double2*>(&sm.Ab[(8 * i0 + 8 + g) * P + 8 * J + 2 * q]) = make_double2(e0, e1);
+    if (WITH_CV) {
+        y0 += __shfl_xor_sync(0xffffffffu, y0, 1);
+        y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
+        if (PAIR) {
+            y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+            y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+        }
+        if (q == 0) {
+            sm.cv[8 * i0 + g] = (y0 - sm.bv[8 * i0 + g]) + theta;
+            if (PAIR) sm.cv[8 * i0 + 8 + g] = (y1 - sm.bv[8 * i0 + 8 + g]) + theta;
+        }
+    }
+}
+// the three A Lt tasks of block column J: tile rows (0,1), (2,3), (4)
+template <bool WITH_CV>
+__device__ __forceinline__ void al_task(EnSmem& sm, int task, int J, double theta, int g, int q)
+{
+    if (task < 2) al_tiles<true, WITH_CV>(sm, 2 * task, J, theta, g, q);
+    else al_tiles<false, WITH_CV>(sm, 4, J, theta, g, q);
+}
+
+// ---- tile-row I of dEsde/dS = (c/2) Vt^T diag(dw) Vt (lower tiles J <= I), mirrored on store,
+//      and entries 8I..8I+7 of dEsde/dm = (sqrt(c)/2) Vt^T qw ----------------------------------
+__device__ __forceinline__ void deds_row(const EnSmem& sm, double* __restrict__ oEs, double* __restrict__ oEm,
+                                         double sc, double scm, int I, int g, int q)
+{
     const int r = 8 * I + g;
+    {   // lane (g, q): column r, rows 8I + q, +4, ... (Vt is zero above the diagonal)
+        double am = 0.0;
+#pragma unroll 1
+        for (int kr = 8 * I + q; kr < D; kr += 4) am = fma(sm.Wb[kr * P + r], sm.bv[kr], am);
+        am += __shfl_xor_sync(0xffffffffu, am, 1);
+        am += __shfl_xor_sync(0xffffffffu, am, 2);
+        if (q == 0) oEm[r] = scm * am;
+    }
+    // A fragments dw[k] Vt[k][r], k = 8 (I + n) + q (+4): loaded once, shared by every J
+    double af[NB][2];
+    const int nk = NB - I;
 #pragma unroll
+    for (int n = 0; n < NB; ++n)
+        if (n < nk) {
+            const int k0 = 8 * (I + n) + q;
+            af[n][0] = sm.cv[k0] * sm.Wb[k0 * P + r];
+            af[n][1] = sm.cv[k0 + 4] * sm.Wb[(k0 + 4) * P + r];
+        }
+#pragma unroll 1
     for (int J = 0; J <= I; ++J) {
-        double c0 = 0.0, c1 = 0.0;
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: half the dependent chain
+        const double* vb = &sm.Wb[(8 * I + q) * P + 8 * J + g];
 #pragma unroll
-        for (int Kb = I; Kb < NB; ++Kb)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) dmma(c0, c1, a[Kb - I][h], sm.Wb[(8 * Kb + 4 * h + q) * P + 8 * J + g]);
+        for (int n = 0; n < NB; ++n)
+            if (n < nk) {
+                dmma(c0, c1, af[n][0], vb[(8 * n) * P]);
+                dmma(e0, e1, af[n][1], vb[(8 * n + 4) * P]);
+            }
         const int cc = 8 * J + 2 * q;
-        const double v0 = sc * c0, v1 = sc * c1;
+        const double v0 = sc * (c0 + e0), v1 = sc * (c1 + e1);
         if (I != J) {
             *reinterpret_cast<double2*>(&oEs[r * D + cc]) = make_double2(v0, v1);
             oEs[cc * D + r] = v0;
@@ -336,20 +379,51 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     const double w0 = kap / c, wi = 1.0 / (2.0 * c);          // :290-291
 
     PROF_INIT();
-    if (tid == 0) {
-        sm.bad = 0;
-        mbar_init(&sm.bar, 1);
-        mbar_fence_init();
+    if (tid == 0) sm.bad = 0;
+    // S(t) (lower block triangle), A(t), m(t), b(t) by 16-byte cp.async copies (SASS LDGSTS):
+    // thread (r0, ch) = (tid / 20, tid % 20) copies chunk ch of rows r0, r0 + 6, ... (82 small
+    // bulk copies per CTA were measured slower: the TMA unit serialises them)
+    if (tid < 120) {
+        const int r0 = tid / 20, ch = tid - r0 * 20;
+        const double* sg_ = St + r0 * D + 2 * ch;
+        const double* ag_ = At + r0 * D + 2 * ch;
+        double* ss_ = sm.Cb + r0 * P + 2 * ch;
+        double* as_ = sm.Ab + r0 * P + 2 * ch;
+#pragma unroll
+        for (int n = 0; n < 7; ++n) {
+            const int row = r0 + 6 * n;
+            if (row < D) {
+                if (ch < 4 * ((row >> 3) + 1)) cp_async16(ss_ + 6 * n * P, sg_ + 6 * n * D);
+                cp_async16(as_ + 6 * n * P, ag_ + 6 * n * D);
+            }
+        }
+    } else {
+        const int u = tid - 120;   // 8 threads: the two 40-vectors (20 chunks each)
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+            const int c2 = u + 8 * n;
+            if (c2 < 20) cp_async16(sm.mv + 2 * c2, mt + 2 * c2);
+            else cp_async16(sm.bv + 2 * (c2 - 20), bt + 2 * (c2 - 20));
+        }
     }
-    __syncthreads();
-    // S(t) (lower block triangle: row r brings columns 0 .. 8 (r/8 + 1) - 1), A(t), m(t), b(t)
-    if (tid == 0) mbar_arrive_expect_tx(&sm.bar, LOAD_BYTES);
-    if (tid < D) bulk_g2s(sm.Cb + tid * P, St + tid * D, 64 * ((tid >> 3) + 1), &sm.bar);
-    else if (tid < 2 * D) bulk_g2s(sm.Ab + (tid - D) * P, At + (tid - D) * D, ROWB, &sm.bar);
-    else if (tid == 2 * D) bulk_g2s(sm.mv, mt, ROWB, &sm.bar);
-    else if (tid == 2 * D + 1) bulk_g2s(sm.bv, bt, ROWB, &sm.bar);
-    // while the copies fly: zero the strict upper tiles of the L and V buffers (the copies do
-    // not touch them), 1 / sigma
+    cp_async_commit();
+    // pull the inputs of the item that will follow this one in its SM slot (148 SMs x 5 CTAs
+    // further down the grid) into L2: its load phase then sees L2 instead of HBM latency
+    {
+        constexpr int AHEAD = 148 * 5;
+        const long long nb = (long long)blockIdx.x + AHEAD;
+        if (nb < (long long)gridDim.x) {
+            if (tid >= 2 * D && tid < 3 * D) {
+                const int r = tid - 2 * D;
+                bulk_prefetch_l2(s.st + nb * (D * D) + r * D, 64 * ((r >> 3) + 1));
+            } else if (tid == 3 * D) {
+                const int lpn = (int)(nb / N), tn = (int)(nb - (long long)lpn * N);
+                bulk_prefetch_l2(x + (long long)(p0 + lpn) * xs + (long long)tn * D * D, D * ROWB);
+            }
+        }
+    }
+    // while the copies fly: zero the strict upper tiles of the L buffer (the copies do not touch
+    // them; the residual phase reads whole columns), 1 / sigma
     {
         const double2 z = make_double2(0.0, 0.0);
 #pragma unroll
@@ -359,12 +433,12 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
                 const int r = e / npair, cp = e - r * npair;
                 const int o = (8 * I + r) * P + 8 * (I + 1) + 2 * cp;
                 *reinterpret_cast<double2*>(&sm.Cb[o]) = z;
-                *reinterpret_cast<double2*>(&sm.Wb[o]) = z;
             }
         }
     }
     if (tid < D) sm.isg[tid] = 1.0 / b.sigma[p * b.sigma_stride + tid];
-    mbar_wait(&sm.bar, 0u);
+    cp_async_wait<0>();
+    __syncthreads();
     PROF_MARK(0);
 
     // <f>, <df/dx> for vgpa_eval_full (lorenz_96.py:34-83,440-462); S is still intact (lower part)
@@ -388,36 +462,60 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     // m +- sdv_j Lt[:, j] with sdv_j = sqrt(c dd_j), and V = chol(S)^-1 = diag(dd^-1/2) Vt, so the
     // square roots only ever appear as per-column scalars of the consumers.
     // ---- blocked factorisation; Vt = Lt^-1 and A Lt grow in its shadow ---------------------
-    if (warp == 0) factor_diag(sm, 0, lane);
-    else if (tid - 32 < D) {
-        // cv = A m - b + theta (A is still intact), in the shadow of the first diagonal block
-        const int r = tid - 32;
-        const double* ar = sm.Ab + r * P;
-        double y0 = 0.0, y1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k += 2) {
-            const double2 a2 = *reinterpret_cast<const double2*>(&ar[k]);
-            y0 = fma(a2.x, sm.mv[k], y0);
-            y1 = fma(a2.y, sm.mv[k + 1], y1);
+    // Block loop (not unrolled).  Warp 0 runs the serial spine and NEVER waits for the others
+    // except for data it needs: per block kb it updates the diagonal tile, factors it, announces it
+    // (named barrier B1, arrive), computes its own panel tile (kb+1, kb) (announced on B2) and goes
+    // on.  Warps 1-3 follow one step behind: wait for B1, their panel tiles, B2 (all panels of the
+    // column are in place), the trailing update of step kb (announced on B3, which warp 0 checks
+    // just before it touches tiles of the next column), and then, in the shadow of the spine, what
+    // has just become final: block row kb of Vt and block column kb of A Lt.
+    if (warp == 0) {
+#pragma unroll 1
+        for (int kb = 0; kb < NB; ++kb) {
+            if (kb > 0) {
+                trail_tile(sm, kb, kb, kb - 1, g, q);
+                __syncwarp();
+            }
+            factor_diag(sm, kb, lane);
+            if (kb < NB - 1) {
+                if (kb & 1) bar_arrive<2>();                   // B1 (ids 1, 2 alternate): Tt_kk, Lt_kk, dd, rp
+                else bar_arrive<1>();                          //     of block kb are in place
+                if (kb > 0) bar_sync<4>();                     // B3: trailing update of step kb-1 complete
+                panel_tile(sm, kb + 1, kb, g, q);
+                bar_arrive<3>();                               // B2: my panel tile is in place
+                __syncwarp();
+            }
         }
-        sm.cv[r] = ((y0 + y1) - sm.bv[r]) + theta;
+    } else {
+#pragma unroll 1
+        for (int kb = 0; kb < NB - 1; ++kb) {
+            if (kb & 1) bar_sync<2>();                         // B1
+            else bar_sync<1>();
+            if (warp < NB - 1 - kb) panel_tile(sm, kb + 1 + warp, kb, g, q);
+            bar_sync<3>();                                     // B2
+            int n = 3 - warp;           // round-robin over warps 1..3: a task is mine when n hits 3
+            for (int i = kb + 2; i < NB; ++i)
+                for (int j = kb + 1; j <= i; ++j)
+                    if (++n == 3) { n = 0; trail_tile(sm, i, j, kb, g, q); }
+            if (kb < NB - 2) bar_arrive<4>();                  // B3
+            for (int j = 0; j < kb; ++j)
+                if (++n == 3) { n = 0; v_tile(sm, kb, j, g, q); }
+            // A Lt, block column kb: three tasks (tile rows (0,1), (2,3), (4)); column 0 also gives cv
+            for (int task = 0; task < 3; ++task)
+                if (++n == 3) {
+                    n = 0;
+                    if (kb == 0) al_task<true>(sm, task, kb, theta, g, q);
+                    else al_task<false>(sm, task, kb, theta, g, q);
+                }
+        }
     }
     PROF_MARK(1);
     __syncthreads();
-    factor_step<0>(sm, warp, lane, g, q);
     PROF_MARK(2);
-    factor_step<1>(sm, warp, lane, g, q);
-    PROF_MARK(3);
-    factor_step<2>(sm, warp, lane, g, q);
-    PROF_MARK(4);
-    factor_step<3>(sm, warp, lane, g, q);
-    PROF_MARK(5);
     // ---- what needed the last diagonal block: row 4 of Vt, column 4 of A Lt, the column scales ----
     {
-        if (warp == 0) { v_tile<4, 0>(sm, g, q); al_tile<4>(sm, 4, g, q); }
-        else if (warp == 1) { v_tile<4, 1>(sm, g, q); al_tile<4>(sm, 0, g, q); }
-        else if (warp == 2) { v_tile<4, 2>(sm, g, q); al_tile<4>(sm, 1, g, q); al_tile<4>(sm, 2, g, q); }
-        else { v_tile<4, 3>(sm, g, q); al_tile<4>(sm, 3, g, q); }
+        v_tile(sm, 4, warp, g, q);
+        if (warp < 3) al_task<false>(sm, warp, 4, theta, g, q);
         if (tid < D) {
             const double cd = c * sm.dd[tid];
             sm.sdv[tid] = cd * fast_rsqrt(cd);
@@ -449,7 +547,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         double x0 = fma(sg, Lc[0], sm.mv[0]);
         const double xwrap = fma(sgn, sm.Cb[coln], sm.mv[0]);
         double var = 0.0;
-#pragma unroll
+#pragma unroll 8
         for (int i = 0; i < D; ++i) {
             const double xp1 = (i + 1 < D) ? fma(sg, Lc[(i + 1) * P], sm.mv[i + 1]) : xwrap;
             const double fx = fma(xp1 - xm2, xm1, -x0);                 // lorenz_96.py:85-101 (theta is in cv)
@@ -463,55 +561,39 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     }
     __syncthreads();
     PROF_MARK(9);
+    double* oEm = s.dEm + ((long long)lp * N + t) * D;
+    double* oEs = s.dEs + ((long long)lp * N + t) * D * D;
+    double esde;
     {
-        // Esde(t) = 1/2 sum_k w_k var_k  (fixed order: lanes stride the 81 values; every warp
-        // computes it, so no second barrier is needed before the weights)
+        // Esde(t) = 1/2 sum_k w_k var_k  (fixed order: lanes stride the 81 values).  EVERY warp
+        // computes it and the 40 + 40 weights below and stores them (same values, same addresses),
+        // so only a warp-level sync separates this from the tile products that read them.
         double e = 0.0;
         for (int k = lane; k < K; k += 32) e += (k == 0 ? w0 : wi) * sm.var[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
         e *= 0.5;
-        if (tid == 0) sm.esde = e;
-        if (tid < D) {
-            const int j = tid;
+        esde = e;
+        for (int j = lane; j < D; j += 32) {
             const double vp = sm.var[1 + j], vm = sm.var[1 + D + j];
-            const double dj = sm.dd[j];
             // V = diag(dd^-1/2) Vt: fold the scales into the weights
-            sm.bv[j] = (wi * (vp - vm)) * fast_rsqrt(dj);                       // q_j / sqrt(d_j)
+            sm.bv[j] = (wi * (vp - vm)) * fast_rsqrt(sm.dd[j]);                 // q_j / sqrt(d_j)
             sm.cv[j] = (0.5 * (wi * (vp + vm)) - e * (1.0 / c)) * sm.rp[j];     // d_j-weight / d_j
         }
+        __syncwarp();
     }
-    __syncthreads();
     PROF_MARK(10);
-
-    double* oEm = s.dEm + ((long long)lp * N + t) * D;
-    double* oEs = s.dEs + ((long long)lp * N + t) * D * D;
-    // ---- dEsde/dS = (c/2) V^T diag(d) V = (c/2) Vt^T diag(d / dd) Vt, lower tiles, mirrored ------
+    // ---- dEsde/dS = (c/2) V^T diag(d) V = (c/2) Vt^T diag(d / dd) Vt, lower tiles, mirrored;
+    //      dEsde/dm = (sqrt(c)/2) V^T q ------
     // tile rows by cost (I + 1)(5 - I): warp0: I=2, warp1: I=3, warp2: I=1, warp3: I=0 and 4
     {
-        const double sc = 0.5 * c;
-        if (warp == 0) deds_row<2>(sm, oEs, sc, g, q);
-        else if (warp == 1) deds_row<3>(sm, oEs, sc, g, q);
-        else if (warp == 2) deds_row<1>(sm, oEs, sc, g, q);
-        else {
-            deds_row<0>(sm, oEs, sc, g, q);
-            deds_row<4>(sm, oEs, sc, g, q);
-        }
-    }
-    // ---- dEsde/dm = (sqrt(c)/2) V^T q = (sqrt(c)/2) Vt^T (q / sqrt(dd)); Vt is zero above the
-    //      diagonal, so every thread of a warp runs the same k range ----
-    if (tid < D) {
-        double a0 = 0.0, a1 = 0.0;
-        const int k0 = (warp == 0) ? 0 : 32;
-#pragma unroll 4
-        for (int k = k0; k < D; k += 2) {
-            a0 = fma(sm.Wb[k * P + tid], sm.bv[k], a0);
-            a1 = fma(sm.Wb[(k + 1) * P + tid], sm.bv[k + 1], a1);
-        }
-        oEm[tid] = (0.5 * sqrt(c)) * (a0 + a1);
+        const double sc = 0.5 * c, scm = 0.5 * sqrt(c);
+        const int I = (warp == 0) ? 2 : (warp == 1 ? 3 : (warp == 2 ? 1 : 0));
+        deds_row(sm, oEs, oEm, sc, scm, I, g, q);
+        if (warp == 3) deds_row(sm, oEs, oEm, sc, scm, 4, g, q);
     }
     if (tid == 0) {
-        s.esde_t[(long long)lp * N + t] = sm.esde;
+        s.esde_t[(long long)lp * N + t] = esde;
         if (sm.bad) atomicCAS(&s.status[lp], 0, 1 + t);
     }
     PROF_MARK(11);
@@ -522,7 +604,10 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
 void launch_l96_energy(const Batch& b, const Scratch& s, const double* x, long long xs, int p0, int count,
                        const Extra& ex, cudaStream_t st)
 {
-    const size_t sh = sizeof(EnSmem);
+    size_t sh = sizeof(EnSmem);
+#ifdef VGPA_EN_PROF
+    if (const char* e = getenv("VGPA_EN_EXTRA_SMEM")) sh += (size_t)atoi(e);   // occupancy experiments
+#endif
     cudaFuncSetAttribute(l96_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     const unsigned grid = (unsigned)((long long)count * b.N);
     l96_energy_kernel<<<grid, NTH, sh, st>>>(b, s, x, xs, p0, count, ex);
