@@ -44,6 +44,25 @@ struct Extra {
     double* parts; // (3) E0, Esde, Eobs
 };
 
+// ---- shared-memory layout of a 40 x 40 matrix in the D = 40 kernels -----------------------
+// Rows are contiguous (one bulk / cp.async copy per row); row PAIRS are 84 doubles apart:
+//   address(row, col) = 84 * (row >> 1) + 40 * (row & 1) + col      (1680 doubles per matrix)
+// i.e. pitch 40 plus a cumulative shift of 4 doubles per row pair.  Modulo the 16 8-byte banks a
+// half-warp sees, row r starts at 8 (r & 1) + 4 ((r >> 1) & 3), which makes ALL access shapes of
+// the kernels bank-conflict free (64-bit accesses go out per half-warp, 128-bit per quarter-warp):
+//   DMMA A fragments  (lane (g,q): row R+g,    col C+q)       rows g = 0..3 start at 0, 8, 4, 12
+//   DMMA B fragments  (lane (g,q): row R+q,    col C+g)       same with q and g swapped
+//   accumulator pairs (lane (g,q): row R+g,    cols C+2q, +1 as one 16-byte access)
+//   transposed reads  (lane (g,q): row R+2q+e, col C+g)       rows 2q+e start at 8e + 4q
+// (pitch 44 / 42, used before, made the 16-byte accumulator accesses 2-way conflicted: 22 % of the
+// forward sweep's shared-memory wavefronts, profiles/README.md.)
+constexpr int SM_MAT = 84 * 20;          // doubles per matrix
+constexpr int SM_R8 = 84 * 4;            // offset of 8 rows
+__host__ __device__ constexpr int sm_idx(int row, int col) { return 84 * (row >> 1) + 40 * (row & 1) + col; }
+// B-fragment addressing: element (8 B + 4 h + q, C + g) is at  B * SM_R8 + C + sm_boff(q, g) + h * SM_BH
+__host__ __device__ constexpr int sm_boff(int q, int g) { return 84 * (q >> 1) + 40 * (q & 1) + g; }
+constexpr int SM_BH = 84 * 2;
+
 // ---- launchers (one translation unit each) --------------------------------
 // p0: first problem of the chunk; count: problems in the chunk.
 void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,

@@ -58,8 +58,7 @@ __device__ unsigned long long g_prof[32];
 #endif
 
 constexpr int D = 40;
-constexpr int P = 44;               // pitch (doubles): DMMA fragment loads conflict-free
-constexpr int MAT = D * P;
+constexpr int MAT = SM_MAT;         // skewed layout of common.cuh (sm_idx): every access shape conflict-free
 constexpr int ROWB = D * 8;
 constexpr int K = 2 * D + 1;        // sigma points
 
@@ -131,13 +130,13 @@ __device__ __forceinline__ double fast_rsqrt(double x)
 __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
 {
     double c[8][8];
-    double* tile = &sm.Cb[(8 * kb) * P + 8 * kb];
-    double* tinv = &sm.Wb[(8 * kb) * P + 8 * kb];
+    double* tile = &sm.Cb[kb * SM_R8 + 8 * kb];      // element (8 kb + i, 8 kb + j) = tile[sm_idx(i, j)]
+    double* tinv = &sm.Wb[kb * SM_R8 + 8 * kb];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j <= i; j += 2) {   // warp-uniform (broadcast) 16-byte loads
-            const double2 v = *reinterpret_cast<const double2*>(&tile[i * P + j]);
+            const double2 v = *reinterpret_cast<const double2*>(&tile[sm_idx(i, j)]);
             c[i][j] = v.x;
             if (j + 1 <= i) c[i][j + 1] = v.y;
         }
@@ -180,7 +179,7 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
 #pragma unroll
         for (int m = 0; m < j; ++m) acc = fma(-c[j][m], y[m], acc);
         y[j] = acc;
-        tinv[j * P + cc] = acc;
+        tinv[sm_idx(j, cc)] = acc;
         // ... and my chunk of row j of Lt (explicit ones / zeros)
         {
             double2 pick = make_double2(0.0, 0.0);
@@ -197,7 +196,7 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
             if (lrow == j) mine = pick;
         }
     }
-    *reinterpret_cast<double2*>(&tile[lrow * P + 2 * lch]) = mine;
+    *reinterpret_cast<double2*>(&tile[sm_idx(lrow, 2 * lch)]) = mine;
     sm.dd[8 * kb + cc] = dmine;
     sm.rp[8 * kb + cc] = rmine;
     if (bad) sm.bad = 1;
@@ -223,20 +222,20 @@ __device__ __forceinline__ void factor_diag(EnSmem& sm, int kb, int lane)
 __device__ __forceinline__ void panel_tile(EnSmem& sm, int i, int kb, int g, int q)
 {
     double c0 = 0.0, c1 = 0.0;
-    const double* ca = &sm.Cb[(8 * i + g) * P + 8 * kb];
-    const double* tb = &sm.Wb[(8 * kb + g) * P + 8 * kb];
+    const double* ca = &sm.Cb[sm_idx(8 * i + g, 8 * kb)];
+    const double* tb = &sm.Wb[sm_idx(8 * kb + g, 8 * kb)];
     TILE_MMA(c0, c1, ca[kk], tb[kk]);
     const double2 r = *reinterpret_cast<const double2*>(&sm.rp[8 * kb + 2 * q]);
     // mma.sync consumed every lane's operands: the tile may be overwritten
-    *reinterpret_cast<double2*>(&sm.Cb[(8 * i + g) * P + 8 * kb + 2 * q]) = make_double2(c0 * r.x, c1 * r.y);
+    *reinterpret_cast<double2*>(&sm.Cb[sm_idx(8 * i + g, 8 * kb + 2 * q)]) = make_double2(c0 * r.x, c1 * r.y);
 }
 
 // ---- (c) trailing tile (i, j) -= Lt_ik D_k Lt_jk^T ------------------------------------------
 __device__ __forceinline__ void trail_tile(EnSmem& sm, int i, int j, int kb, int g, int q)
 {
-    double* ct = &sm.Cb[(8 * i + g) * P + 8 * j + 2 * q];
-    const double* la = &sm.Cb[(8 * i + g) * P + 8 * kb];
-    const double* lb = &sm.Cb[(8 * j + g) * P + 8 * kb];
+    double* ct = &sm.Cb[sm_idx(8 * i + g, 8 * j + 2 * q)];
+    const double* la = &sm.Cb[sm_idx(8 * i + g, 8 * kb)];
+    const double* lb = &sm.Cb[sm_idx(8 * j + g, 8 * kb)];
     const double* dk = &sm.dd[8 * kb];
     double2 cc = *reinterpret_cast<double2*>(ct);
     TILE_MMA(cc.x, cc.y, -la[kk] * dk[kk], lb[kk]);
@@ -248,16 +247,16 @@ __device__ __forceinline__ void trail_tile(EnSmem& sm, int i, int j, int kb, int
 __device__ __forceinline__ void v_tile(EnSmem& sm, int I, int J, int g, int q)
 {
     double s0 = 0.0, s1 = 0.0;
-    const double* la = &sm.Cb[(8 * I + g) * P];
-    const double* vb = &sm.Wb[8 * J + g];
+    const double* la = &sm.Cb[sm_idx(8 * I + g, 0)];
+    const double* vb = &sm.Wb[8 * J + sm_boff(q, g)];           // B fragments of block column J
 #pragma unroll 1
-    for (int m = J; m < I; ++m) TILE_MMA(s0, s1, la[8 * m + kk], vb[(8 * m + kk) * P]);
-    double* out = &sm.Wb[(8 * I + g) * P + 8 * J + 2 * q];
+    for (int m = J; m < I; ++m) TILE_MMA(s0, s1, la[8 * m + kk], vb[m * SM_R8 + h * SM_BH]);
+    double* out = &sm.Wb[sm_idx(8 * I + g, 8 * J + 2 * q)];
     *reinterpret_cast<double2*>(out) = make_double2(s0, s1);
     __syncwarp();
     double v0 = 0.0, v1 = 0.0;
-    const double* ta = &sm.Wb[(8 * I + g) * P + 8 * I];
-    TILE_MMA(v0, v1, -ta[kk], vb[(8 * I + kk) * P]);
+    const double* ta = &sm.Wb[sm_idx(8 * I + g, 8 * I)];
+    TILE_MMA(v0, v1, -ta[kk], vb[I * SM_R8 + h * SM_BH]);
     __syncwarp();
     *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
 }
@@ -269,19 +268,19 @@ template <bool PAIR, bool WITH_CV>
 __device__ __forceinline__ void al_tiles(EnSmem& sm, int i0, int J, double theta, int g, int q)
 {
     double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, y0 = 0.0, y1 = 0.0;
-    const double* aa = &sm.Ab[(8 * i0 + g) * P + q];
-    const double* lb = &sm.Cb[q * P + 8 * J + g];
+    const double* aa = &sm.Ab[sm_idx(8 * i0 + g, q)];             // row 8 i0 + 8 + g has the same skew
+    const double* lb = &sm.Cb[8 * J + sm_boff(q, g)];             // B fragments of block column J
 #pragma unroll 1
     for (int Kb = J; Kb < NB; ++Kb) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ko = 8 * Kb + 4 * h;
-            const double bf = lb[ko * P];
+            const double bf = lb[Kb * SM_R8 + h * SM_BH];
             const double a0 = aa[ko];
             dmma(c0, c1, a0, bf);
             double a1 = 0.0;
             if (PAIR) {
-                a1 = aa[8 * P + ko];
+                a1 = aa[SM_R8 + ko];
                 dmma(e0, e1, a1, bf);
             }
             if (WITH_CV) {
@@ -291,8 +290,8 @@ __device__ __forceinline__ void al_tiles(EnSmem& sm, int i0, int J, double theta
             }
         }
     }
-    *reinterpret_cast<double2*>(&sm.Ab[(8 * i0 + g) * P + 8 * J + 2 * q]) = make_double2(c0, c1);
-    if (PAIR) *reinterpret_cast<double2*>(&sm.Ab[(8 * i0 + 8 + g) * P + 8 * J + 2 * q]) = make_double2(e0, e1);
+    *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + g, 8 * J + 2 * q)]) = make_double2(c0, c1);
+    if (PAIR) *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + 8 + g, 8 * J + 2 * q)]) = make_double2(e0, e1);
     if (WITH_CV) {
         y0 += __shfl_xor_sync(0xffffffffu, y0, 1);
         y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
@@ -323,7 +322,7 @@ __device__ __forceinline__ void deds_row(const EnSmem& sm, double* __restrict__ 
     {   // lane (g, q): column r, rows 8I + q, +4, ... (Vt is zero above the diagonal)
         double am = 0.0;
 #pragma unroll 1
-        for (int kr = 8 * I + q; kr < D; kr += 4) am = fma(sm.Wb[kr * P + r], sm.bv[kr], am);
+        for (int kr = 8 * I + q; kr < D; kr += 4) am = fma(sm.Wb[sm_idx(kr, r)], sm.bv[kr], am);
         am += __shfl_xor_sync(0xffffffffu, am, 1);
         am += __shfl_xor_sync(0xffffffffu, am, 2);
         if (q == 0) oEm[r] = scm * am;
@@ -335,18 +334,18 @@ __device__ __forceinline__ void deds_row(const EnSmem& sm, double* __restrict__ 
     for (int n = 0; n < NB; ++n)
         if (n < nk) {
             const int k0 = 8 * (I + n) + q;
-            af[n][0] = sm.cv[k0] * sm.Wb[k0 * P + r];
-            af[n][1] = sm.cv[k0 + 4] * sm.Wb[(k0 + 4) * P + r];
+            af[n][0] = sm.cv[k0] * sm.Wb[(I + n) * SM_R8 + 8 * I + sm_boff(q, g)];
+            af[n][1] = sm.cv[k0 + 4] * sm.Wb[(I + n) * SM_R8 + 8 * I + sm_boff(q, g) + SM_BH];
         }
 #pragma unroll 1
     for (int J = 0; J <= I; ++J) {
         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: half the dependent chain
-        const double* vb = &sm.Wb[(8 * I + q) * P + 8 * J + g];
+        const double* vb = &sm.Wb[I * SM_R8 + 8 * J + sm_boff(q, g)];
 #pragma unroll
         for (int n = 0; n < NB; ++n)
             if (n < nk) {
-                dmma(c0, c1, af[n][0], vb[(8 * n) * P]);
-                dmma(e0, e1, af[n][1], vb[(8 * n + 4) * P]);
+                dmma(c0, c1, af[n][0], vb[n * SM_R8]);
+                dmma(e0, e1, af[n][1], vb[n * SM_R8 + SM_BH]);
             }
         const int cc = 8 * J + 2 * q;
         const double v0 = sc * (c0 + e0), v1 = sc * (c1 + e1);
@@ -387,14 +386,13 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         const int r0 = tid / 20, ch = tid - r0 * 20;
         const double* sg_ = St + r0 * D + 2 * ch;
         const double* ag_ = At + r0 * D + 2 * ch;
-        double* ss_ = sm.Cb + r0 * P + 2 * ch;
-        double* as_ = sm.Ab + r0 * P + 2 * ch;
 #pragma unroll
         for (int n = 0; n < 7; ++n) {
             const int row = r0 + 6 * n;
             if (row < D) {
-                if (ch < 4 * ((row >> 3) + 1)) cp_async16(ss_ + 6 * n * P, sg_ + 6 * n * D);
-                cp_async16(as_ + 6 * n * P, ag_ + 6 * n * D);
+                const int o = sm_idx(row, 2 * ch);
+                if (ch < 4 * ((row >> 3) + 1)) cp_async16(sm.Cb + o, sg_ + 6 * n * D);
+                cp_async16(sm.Ab + o, ag_ + 6 * n * D);
             }
         }
     } else {
@@ -431,7 +429,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             const int npair = 4 * (NB - 1 - I);               // 16-byte pairs per row right of tile I
             for (int e = tid; e < 8 * npair; e += NTH) {
                 const int r = e / npair, cp = e - r * npair;
-                const int o = (8 * I + r) * P + 8 * (I + 1) + 2 * cp;
+                const int o = sm_idx(8 * I + r, 8 * (I + 1) + 2 * cp);
                 *reinterpret_cast<double2*>(&sm.Cb[o]) = z;
             }
         }
@@ -445,8 +443,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     if (ex.Efx != nullptr && lp == 0) {
         for (int i = tid; i < D; i += NTH) {
             const int f1 = (i + 1) % D, b1 = (i + D - 1) % D, b2 = (i + D - 2) % D;
-            const double s1 = sm.Cb[(f1 > b1 ? f1 : b1) * P + (f1 > b1 ? b1 : f1)];
-            const double s2 = sm.Cb[(b2 > b1 ? b2 : b1) * P + (b2 > b1 ? b1 : b2)];
+            const double s1 = sm.Cb[sm_idx(f1 > b1 ? f1 : b1, f1 > b1 ? b1 : f1)];
+            const double s2 = sm.Cb[sm_idx(b2 > b1 ? b2 : b1, b2 > b1 ? b1 : b2)];
             ex.Efx[(long long)t * D + i] = (s1 - s2) + (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] - sm.mv[i] + theta;
             double* row = ex.Edf + (long long)t * D * D + (long long)i * D;
             for (int j = 0; j < D; ++j) row[j] = 0.0;
@@ -542,16 +540,16 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         const double* Lc = sm.Cb + col;
         const double* ALc = sm.Ab + col;
         // the flattened roll (lorenz_96.py:27-32) wraps into the neighbouring sigma points
-        double xm2 = fma(sgp, sm.Cb[(D - 2) * P + colp], sm.mv[D - 2]);
-        double xm1 = fma(sgp, sm.Cb[(D - 1) * P + colp], sm.mv[D - 1]);
+        double xm2 = fma(sgp, sm.Cb[sm_idx(D - 2, colp)], sm.mv[D - 2]);
+        double xm1 = fma(sgp, sm.Cb[sm_idx(D - 1, colp)], sm.mv[D - 1]);
         double x0 = fma(sg, Lc[0], sm.mv[0]);
         const double xwrap = fma(sgn, sm.Cb[coln], sm.mv[0]);
         double var = 0.0;
 #pragma unroll 8
         for (int i = 0; i < D; ++i) {
-            const double xp1 = (i + 1 < D) ? fma(sg, Lc[(i + 1) * P], sm.mv[i + 1]) : xwrap;
+            const double xp1 = (i + 1 < D) ? fma(sg, Lc[sm_idx(i + 1, 0)], sm.mv[i + 1]) : xwrap;
             const double fx = fma(xp1 - xm2, xm1, -x0);                 // lorenz_96.py:85-101 (theta is in cv)
-            const double r = fx + fma(sg, ALc[i * P], sm.cv[i]);
+            const double r = fx + fma(sg, ALc[sm_idx(i, 0)], sm.cv[i]);
             var = fma(sm.isg[i] * r, r, var);
             xm2 = xm1;
             xm1 = x0;
