@@ -35,11 +35,8 @@ namespace vgpa {
 namespace {
 
 constexpr int D = 40;
-constexpr int P = 44;          // shared-memory row pitch (doubles): 352 B rows, 16 B aligned,
-                               // 2P mod 32 = 24 -> DMMA A/B fragment loads hit 16 distinct banks
-constexpr int MAT = D * P;     // one padded matrix
-constexpr int PT = 42;         // pitch of the transpose-exchange buffer: 4 PT mod 32 = 8 makes the
-                               // transposed reads (rows 2q+e, column 8w+g) conflict-free
+constexpr int MAT = SM_MAT;    // one matrix in the skewed layout of common.cuh (sm_idx): fragment loads,
+                               // accumulator-layout 16-byte accesses and transposed reads all conflict-free
 constexpr int ROWB = D * 8;    // bytes of one matrix row in HBM
 constexpr int NMMA = 5;        // MMA warps = tile rows
 constexpr int NTH = 32 * NMMA;
@@ -100,9 +97,9 @@ __device__ __forceinline__ void mma_row(const double* __restrict__ L0, const dou
 #pragma unroll
     for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
     double y = 0.0;
-    const int la = irow * P + q;   // A fragment: row irow, col k0+q
-    const int lb = q * P + g;      // B fragment: row k0+q, col 8J+g
-#pragma unroll 5
+    const int la = sm_idx(irow, q);   // A fragment: row irow, col k0+q
+    const int lb = sm_boff(q, g);     // B fragment: row k0+q, col 8J+g
+#pragma unroll
     for (int k0 = 0; k0 < D; k0 += 4) {
         double a, av = 0.0;
         if (LK == 0) a = L0[la + k0];
@@ -120,7 +117,7 @@ __device__ __forceinline__ void mma_row(const double* __restrict__ L0, const dou
         double b[5];
 #pragma unroll
         for (int J = 0; J < 5; ++J) {
-            const int o = lb + k0 * P + 8 * J;
+            const int o = lb + (k0 >> 3) * SM_R8 + ((k0 >> 2) & 1) * SM_BH + 8 * J;
             if (RK == 0) b[J] = R0[o];
             else b[J] = 0.5 * (R0[o] + R1[o]);
         }
@@ -139,7 +136,7 @@ __device__ __forceinline__ void row_to_smem(double* __restrict__ T, int irow, in
 {
 #pragma unroll
     for (int J = 0; J < 5; ++J)
-        *reinterpret_cast<double2*>(&T[irow * PT + 8 * J + 2 * q]) = make_double2(acc[J][0], acc[J][1]);
+        *reinterpret_cast<double2*>(&T[sm_idx(irow, 8 * J + 2 * q)]) = make_double2(acc[J][0], acc[J][1]);
 }
 
 template <int KIND>
@@ -151,7 +148,7 @@ __device__ __forceinline__ double pick(double c, double n)
 // every warp issues the bulk copies of its own 8 rows of a 40 x 40 matrix
 __device__ __forceinline__ void load_rows(double* dst, const double* src, uint64_t* bar, int w, int lane)
 {
-    if (lane < 8) bulk_g2s(dst + (8 * w + lane) * P, src + (8 * w + lane) * D, ROWB, bar);
+    if (lane < 8) bulk_g2s(dst + sm_idx(8 * w + lane, 0), src + (8 * w + lane) * D, ROWB, bar);
 }
 
 // ===========================================================================
@@ -165,7 +162,7 @@ __device__ __forceinline__ void load_rows(double* dst, const double* src, uint64
 // transpose exchange (42 KB), so four CTAs share an SM.
 struct FwdSmem {
     double Sb[MAT], Hb[MAT];
-    double Tb[D * PT];
+    double Tb[MAT];
     double mv[D], vt[2][D], sig[D];
 };
 
@@ -180,8 +177,8 @@ __device__ __forceinline__ void mma_rowa(const double (&A0)[D / 4], const double
 #pragma unroll
     for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
     double y = 0.0;
-    const int la = irow * P + q;
-    const int lb = q * P + g;
+    const int la = sm_idx(irow, q);
+    const int lb = sm_boff(q, g);
 #pragma unroll
     for (int n = 0; n < D / 4; ++n) {
         const int k0 = 4 * n;
@@ -195,7 +192,7 @@ __device__ __forceinline__ void mma_rowa(const double (&A0)[D / 4], const double
         y = fma(av, v[k0 + q], y);
         double b[5];
 #pragma unroll
-        for (int J = 0; J < 5; ++J) b[J] = X[lb + k0 * P + 8 * J];
+        for (int J = 0; J < 5; ++J) b[J] = X[lb + (n >> 1) * SM_R8 + (n & 1) * SM_BH + 8 * J];
 #pragma unroll
         for (int J = 0; J < 5; ++J) dmma(acc[J][0], acc[J][1], a, b[J]);
     }
@@ -225,7 +222,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     for (int e = tid; e < D * D; e += NTH) {
         const int i = e / D, j = e % D;
         const double v = b.s0[p * b.s0_stride + e];
-        sm.Sb[i * P + j] = v;
+        sm.Sb[sm_idx(i, j)] = v;
         st[e] = v;
     }
     if (tid < D) {
@@ -281,12 +278,12 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 #pragma unroll
                 for (int J = 0; J < 5; ++J) {
                     const int j0 = 8 * J + 2 * q;
-                    const double2 sv = *reinterpret_cast<const double2*>(&sm.Sb[i * P + j0]);
+                    const double2 sv = *reinterpret_cast<const double2*>(&sm.Sb[sm_idx(i, j0)]);
                     double out[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int j = j0 + e;
-                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[j * PT + i]);
+                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[sm_idx(j, i)]);
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
                         const double sold = e == 0 ? sv.x : sv.y;
@@ -294,9 +291,9 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                         else out[e] = sold + final_step<METHOD>(dt, ksum[J][e]);
                     }
                     if (sidx < NS - 1) {
-                        *reinterpret_cast<double2*>(&sm.Hb[i * P + j0]) = make_double2(out[0], out[1]);
+                        *reinterpret_cast<double2*>(&sm.Hb[sm_idx(i, j0)]) = make_double2(out[0], out[1]);
                     } else {
-                        *reinterpret_cast<double2*>(&sm.Sb[i * P + j0]) = make_double2(out[0], out[1]);
+                        *reinterpret_cast<double2*>(&sm.Sb[sm_idx(i, j0)]) = make_double2(out[0], out[1]);
                         *reinterpret_cast<double2*>(&st[(long long)(k + 1) * D * D + i * D + j0]) =
                             make_double2(out[0], out[1]);
                     }
@@ -327,7 +324,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 // transpose exchange -- which lets 3 CTAs share an SM and needs one barrier per stage.
 struct BwdSmem {
     double Ab[2][MAT], Sb[MAT];
-    double Tb[2][D * PT];
+    double Tb[2][MAT];
     double mv[D], bv[D], lam[D], lt[2][D], isg[D], Rv[D];
     uint64_t barA[2], barS;
 };
@@ -359,8 +356,8 @@ __device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double 
 #pragma unroll
     for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
     double y = 0.0;
-    const int la = irow * P + q;
-    const int lb = q * P + g;
+    const int la = sm_idx(irow, q);
+    const int lb = sm_boff(q, g);
     const int srcb = (lane & ~3) + (q >> 1);
     const bool odd = (q & 1) != 0;
 #pragma unroll
@@ -385,7 +382,7 @@ __device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double 
         double b[5];
 #pragma unroll
         for (int J = 0; J < 5; ++J) {
-            const int o = lb + k0 * P + 8 * J;
+            const int o = lb + (n >> 1) * SM_R8 + (n & 1) * SM_BH + 8 * J;
             if (RK == 0) b[J] = R0[o];
             else b[J] = 0.5 * (R0[o] + R1[o]);
         }
@@ -515,7 +512,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             // W = (Sigma^-1 (A_t + <df/dx>) - 2 Psi_t) S_t   and   am = (A_t m_t)[irow]
             mma_rowx<2, 0, 3>(Pc, edf, Ac, sm.Sb, nullptr, nullptr, nullptr, sm.mv, sm.isg[irow], irow, g, q, lane, acc, am);
             // <f> of Lorenz 96 (lorenz_96.py:440-462)
-            const double Ef = (sm.Sb[f1 * P + b1] - sm.Sb[b2 * P + b1]) + (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] -
+            const double Ef = (sm.Sb[sm_idx(f1, b1)] - sm.Sb[sm_idx(b2, b1)]) + (sm.mv[f1] - sm.mv[b2]) * sm.mv[b1] -
                               sm.mv[i] + theta;
             const double db = sm.isg[i] * (-Ef - am + sm.bv[i]);   // variational.py:324-334
             const double ui = db + sm.lam[i];
@@ -594,7 +591,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                         if (kind == K_CUR) gg = Gc[J][e];
                         else if (kind == K_NEXT) gg = Gn[J][e];
                         else gg = 0.5 * (Gn[J][e] + Gc[J][e]);
-                        const double kk = -gg + (acc[J][e] + Tw[j * PT + i]);  // ode_solver.py:94
+                        const double kk = -gg + (acc[J][e] + Tw[sm_idx(j, i)]);  // ode_solver.py:94
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
                         if (sidx < NS - 1) Hc[J][e] = Pc[J][e] - (next_coef(METHOD, sidx) * dt) * kk;
