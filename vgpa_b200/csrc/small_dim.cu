@@ -121,12 +121,21 @@ small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
 #pragma unroll
     for (int i = 0; i < DD; ++i) st[i] = S[i];
     const double dt = b.dt, h = 0.5 * dt;
-    double Ak[DD], bk[D], An[DD], bn[D];
+    // A(k), b(k) of the current index, of the next one (loaded a step ago) and of the one after
+    // (load issued now): with one thread per problem nothing else hides the global-load latency
+    double Ak[DD], bk[D], An[DD], bn[D], Af[DD], bf[D];
     ld_vec<DD>(A, Ak);
     ld_vec<D>(bo, bk);
+    if (N > 1) {
+        ld_vec<DD>(A + DD, An);
+        ld_vec<D>(bo + D, bn);
+    }
     for (int k = 0; k < N - 1; ++k) {
-        ld_vec<DD>(A + (long long)(k + 1) * DD, An);
-        ld_vec<D>(bo + (long long)(k + 1) * D, bn);
+        {
+            const int kf = (k + 2 < N) ? k + 2 : N - 1;
+            ld_vec<DD>(A + (long long)kf * DD, Af);
+            ld_vec<D>(bo + (long long)kf * D, bf);
+        }
         double mn[D], Sn[DD];
         if (METHOD == ODE_EULER) {  // euler.py:84-87
             double v1[D], k1[DD];
@@ -188,12 +197,14 @@ small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
         for (int i = 0; i < D; ++i) {
             m[i] = mn[i];
             bk[i] = bn[i];
+            bn[i] = bf[i];
             mt[(long long)(k + 1) * D + i] = mn[i];
         }
 #pragma unroll
         for (int i = 0; i < DD; ++i) {
             S[i] = Sn[i];
             Ak[i] = An[i];
+            An[i] = Af[i];
             st[(long long)(k + 1) * DD + i] = Sn[i];
         }
     }
@@ -445,16 +456,35 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
     for (int i = 0; i < D; ++i) lam[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < DD; ++i) Psi[i] = 0.0;
-    double At[DD], gt[D], Gt[DD];
+    // Register prefetch, as in the forward sweep: index t (current), t-1 (loaded a step ago) and
+    // t-2 (load issued at the top of the step) for A, dE/dm, dE/dS; t and t-1 for m, S, b.
+    double At[DD], gt[D], Gt[DD], Am[DD], gm[D], Gm[DD], Af[DD], gf[D], Gf[DD];
+    double m[D], S[DD], bt[D], mp[D], Sp[DD], bp[D];
     ld_vec<DD>(A + (long long)(N - 1) * DD, At);
     ld_vec<D>(dEm + (long long)(N - 1) * D, gt);
     ld_vec<DD>(dEs + (long long)(N - 1) * DD, Gt);
+    {
+        const int t1 = (N >= 2) ? N - 2 : 0;
+        ld_vec<DD>(A + (long long)t1 * DD, Am);
+        ld_vec<D>(dEm + (long long)t1 * D, gm);
+        ld_vec<DD>(dEs + (long long)t1 * DD, Gm);
+    }
+    if (gA != nullptr) {
+        ld_vec<D>(mt + (long long)(N - 1) * D, m);
+        ld_vec<DD>(st + (long long)(N - 1) * DD, S);
+        ld_vec<D>(bo + (long long)(N - 1) * D, bt);
+    }
     for (int t = N - 1; t >= 0; --t) {
-        double m[D], S[DD], bt[D];
-        if (gA != nullptr) {
-            ld_vec<D>(mt + (long long)t * D, m);
-            ld_vec<DD>(st + (long long)t * DD, S);
-            ld_vec<D>(bo + (long long)t * D, bt);
+        {
+            const int t2 = (t >= 2) ? t - 2 : 0, t1 = (t >= 1) ? t - 1 : 0;
+            ld_vec<DD>(A + (long long)t2 * DD, Af);
+            ld_vec<D>(dEm + (long long)t2 * D, gf);
+            ld_vec<DD>(dEs + (long long)t2 * DD, Gf);
+            if (gA != nullptr) {
+                ld_vec<D>(mt + (long long)t1 * D, mp);
+                ld_vec<DD>(st + (long long)t1 * DD, Sp);
+                ld_vec<D>(bo + (long long)t1 * D, bp);
+            }
         }
         if (keep) {
 #pragma unroll
@@ -471,10 +501,6 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
             for (int i = 0; i < D; ++i) gb[(long long)t * D + i] = gbv[i];
         }
         if (t == 0) break;
-        double Am[DD], gm[D], Gm[DD];
-        ld_vec<DD>(A + (long long)(t - 1) * DD, Am);
-        ld_vec<D>(dEm + (long long)(t - 1) * D, gm);
-        ld_vec<DD>(dEs + (long long)(t - 1) * DD, Gm);
         // jump at index t-1 (gaussian_like.py:188,191 / :235,238); H = I, R diagonal
         double jm[D], js[D];
         const int n = dense ? -1 : b.obs_index[t - 1];
@@ -486,7 +512,8 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
         if (n >= 0) {
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                jm[i] = -(oy[(long long)n * D + i] - mt[(long long)(t - 1) * D + i]) / Rv[i];
+                const double mprev = (gA != nullptr) ? mp[i] : mt[(long long)(t - 1) * D + i];
+                jm[i] = -(oy[(long long)n * D + i] - mprev) / Rv[i];
                 js[i] = 0.5 / Rv[i];
             }
         }
@@ -563,12 +590,18 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
         for (int i = 0; i < D; ++i) {
             lam[i] = ln[i];
             gt[i] = gm[i];
+            gm[i] = gf[i];
+            m[i] = mp[i];
+            bt[i] = bp[i];
         }
 #pragma unroll
         for (int i = 0; i < DD; ++i) {
             Psi[i] = Pn[i];
             At[i] = Am[i];
+            Am[i] = Af[i];
             Gt[i] = Gm[i];
+            Gm[i] = Gf[i];
+            S[i] = Sp[i];
         }
     }
 }
