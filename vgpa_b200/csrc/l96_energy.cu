@@ -18,22 +18,24 @@
 // l96() on the 81 x 40 sigma-point matrix uses numba's FLATTENED np.roll
 // (lorenz_96.py:27-32,85-101): neighbours wrap across adjacent sigma points.
 //
-// Blocked algorithm on 8 x 8 tiles (5 x 5 tile grid).  Scalar FP64 instructions and DMMA
-// share ONE pipe on sm_100a (a warp-wide DFMA costs 2.26 pipe cycles whatever the lane
-// mask, a DMMA 16: profiles/microbench_r02.jsonl), so everything that can be a tile
-// product is one, and all tile loops are unrolled at compile time (immediate offsets):
-//   load : the lower block triangle of S(t) and A(t), m(t), b(t) by 1-D bulk async copies
-//          (TMA unit, SASS UBLKCP) on one mbarrier; the upper tiles of the L and V buffers
-//          are zero-filled while the copies are in flight
-//   for k = 0..4:  (a) diagonal block by one warp, the whole lower triangle in the registers
-//                      of every lane: L_kk (LDL^T with hardware-seeded reciprocals) AND its
-//                      inverse T_kk = L_kk^-1 (lane c solves column c) -- the serial spine
-//                  (b) panel L_ik = C_ik T_kk^T as DMMA tile products (i > k)
-//                  (c) trailing C_ij -= L_ik L_jk^T as DMMA tiles, with look-ahead: the next
-//                      diagonal block is factored while the other warps finish (c)
-//   V = L^-1: diagonal tiles are the T_kk; block column j by warp j as DMMA tile products
-//   A L in place over A (and A m);  81 residual energies, one thread per sigma point;
-//   V^T diag(d) V on the lower tiles, mirrored on store.
+// Blocked algorithm on 8 x 8 tiles (5 x 5 tile grid), LDL^T form: S = Lt D Lt^T with Lt unit
+// lower, Vt = Lt^-1; chol(c S) = Lt diag(sqrt(c d)) and V = diag(d^-1/2) Vt, so square roots only
+// appear as per-column scalars of the consumers.  Scalar FP64 instructions and DMMA share ONE pipe
+// on sm_100a (a warp-wide DFMA costs 2.26 pipe cycles whatever the lane mask, a DMMA 16:
+// profiles/microbench_r01.jsonl), so everything that can be a tile product is one.  One item is
+// LATENCY bound by its serial spine, the five diagonal blocks (tools/energy_prof.cu), hence:
+//   load : lower block triangle of S(t), A(t), m(t), b(t) by 16-byte cp.async copies; the upper
+//          tiles of the Lt buffer are zero-filled while the copies are in flight
+//   spine (warp 0, never waits at a CTA barrier): for k = 0..4 update the diagonal tile, factor it
+//          with the whole lower triangle in the registers of every lane (redundant, branch-free;
+//          lane c also solves column c of Tt_kk = Lt_kk^-1), announce it (named barrier, arrive),
+//          compute its own panel tile (k+1, k)
+//   followers (warps 1-3, one step behind): panels Lt_ik = C_ik Tt_kk^T D_k^-1 as DMMA tile
+//          products, trailing C_ij -= Lt_ik D_k Lt_jk^T, then in the shadow of the spine block
+//          row k of Vt and block column k of A Lt (in place over A; column 0 also gives A m)
+//   81 residual energies, one thread per sigma point;
+//   Vt^T diag(w / d) Vt on the lower tiles, mirrored on store; dE/dm from the same columns.
+// Shared-memory layout: common.cuh sm_idx (conflict-free for every access shape used here).
 #include "common.cuh"
 #include "ptx.cuh"
 
