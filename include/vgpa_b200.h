@@ -152,7 +152,11 @@ int vgpa_solve_bwd(int device, int method, int D, int N, double dt, const double
 int vgpa_model_energy(int device, int model, int D, int N, double dt_model, const double *theta,
                       const double *sigma, const double *A, const double *b, const double *m,
                       const double *S, double *Esde, double *Ef, double *Edf, double *dEsde_dm,
-                      double *dEsde_ds);
+                      double *dEsde_ds, double *dEsde_dtheta, double *dEsde_dsigma);
+/* dEsde_dtheta / dEsde_dsigma: the hyper-parameter gradients that energy() returns last
+ * (double_well.py:251-257, ornstein_uhlenbeck.py:223-229, lorenz_63.py:327-343 + :572-633,
+ * lorenz_96.py:420-434) and VarGP discards.  Both may be NULL (not computed).  Sizes:
+ * dEsde_dtheta 1 (DW, OU), 3 (L63), D (L96); dEsde_dsigma 1 (D = 1) or D x D. */
 
 /* GaussianLikelihood.__call__ and .gradients (gaussian_like.py:39-243) on their
  * own: one problem, HOST buffers, identity operator, diagonal R (D values).
@@ -160,7 +164,9 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
  * dEobs_ds (N,D,D), zero except at obs_t. */
 int vgpa_obs_energy(int device, int D, int N, int M, const int64_t *obs_t, const double *obs_y,
                     const double *R, const double *mt, const double *st, double *Eobs,
-                    double *dEobs_dm, double *dEobs_ds);
+                    double *dEobs_dm, double *dEobs_ds, double *dEobs_dr);
+/* dEobs_dr (may be NULL): third output of GaussianLikelihood.gradients -- N values for D = 1
+ * (gaussian_like.py:194), N x M x M zeros for D > 1 (the reference never fills it, :226). */
 
 /* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
 void *vgpa_host_alloc(int64_t bytes);

@@ -133,6 +133,10 @@ class Oracle:
         L.oracle_bwd.argtypes = [C.POINTER(_CProblem)] + [_dp] * 7
         L.oracle_energy.restype = C.c_int
         L.oracle_energy.argtypes = [C.POINTER(_CProblem)] + [_dp] * 9
+        L.oracle_energy_hyper.restype = C.c_int
+        L.oracle_energy_hyper.argtypes = [C.POINTER(_CProblem)] + [_dp] * 5
+        L.oracle_eobs_dr.restype = None
+        L.oracle_eobs_dr.argtypes = [C.POINTER(_CProblem), _dp, _dp, _dp]
         L.oracle_eobs.restype = C.c_double
         L.oracle_eobs.argtypes = [C.POINTER(_CProblem), _dp, _dp]
         L.oracle_eobs_grad.restype = None
@@ -175,6 +179,27 @@ class Oracle:
             outs[k] = outs[k].reshape(shp_m if k in ("st", "psit", "Edf", "dEsde_ds") else shp_v)
         outs.update(F=float(F[0]), E0=parts[0], Esde=parts[1], Eobs=parts[2], grad=grad)
         return outs
+
+    def energy_hyper(self, prob, x, mt, st):
+        """dEsde_dtheta, dEsde_dsigma of model.energy (reference shapes)."""
+        D, N = prob.D, prob.N
+        nth = {"DW": 1, "OU": 1, "L63": 3, "L96": D}[prob.model.upper()]
+        x, mt, st = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, mt, st))
+        dth, dsig = np.zeros(nth), np.zeros(1 if D == 1 else D * D)
+        cp = prob.c_struct()
+        self._raise(self.lib.oracle_energy_hyper(C.byref(cp), _p(x), _p(mt), _p(st), _p(dth), _p(dsig)))
+        if D == 1:
+            return float(dth[0]), float(dsig[0])
+        return dth, dsig.reshape(D, D)
+
+    def eobs_dr(self, prob, mt, st):
+        """dEobs_dr of GaussianLikelihood.gradients."""
+        D, N, M = prob.D, prob.N, len(np.atleast_1d(prob.obs_t))
+        mt, st = (np.ascontiguousarray(a, dtype=np.float64) for a in (mt, st))
+        dr = np.zeros(N if D == 1 else N * M * M)
+        cp = prob.c_struct()
+        self.lib.oracle_eobs_dr(C.byref(cp), _p(mt), _p(st), _p(dr))
+        return dr if D == 1 else dr.reshape(N, M, M)
 
     def eval_batch(self, probs, X, want_grad=True, threads=0):
         """X: (B, n) one evaluation point per problem."""

@@ -705,6 +705,164 @@ int oracle_energy(const oracle_problem *p, const double *x, const double *mt,
 }
 
 /* ------------------------------------------------------------------------ */
+/* Hyper-parameter gradients of model.energy (the last two entries of its     */
+/* third return value; VarGP discards them, variational.py:175):              */
+/*   DW  double_well.py:251-257      OU  ornstein_uhlenbeck.py:223-229         */
+/*   L63 lorenz_63.py:327-343 with Efg_drift_theta :572-633                    */
+/*   L96 lorenz_96.py:420-434                                                  */
+/* dth: 1 (DW, OU), 3 (L63), D (L96) values; dsig: 1 value (D = 1) or D x D.   */
+/* ------------------------------------------------------------------------ */
+static void l63_theta_step(const double *th, const double *at, const double *bt,
+                           const double *mt, const double *st, double *V)
+{ /* lorenz_63.py:587-633 (reads the UPPER triangle of S) */
+    const double vS = th[0], vR = th[1], vB = th[2];
+    const double A11 = at[0], A12 = at[1], A13 = at[2], A21 = at[3], A22 = at[4],
+                 A23 = at[5], A31 = at[6], A32 = at[7], A33 = at[8];
+    const double b1 = bt[0], b2 = bt[1], b3 = bt[2];
+    const double mx = mt[0], my = mt[1], mz = mt[2];
+    const double Sxx = st[0], Sxy = st[1], Sxz = st[2], Syy = st[4], Syz = st[5], Szz = st[8];
+    const double Exx = Sxx + mx * mx, Exy = Sxy + mx * my, Eyy = Syy + my * my;
+    const double Exz = Sxz + mx * mz, Ezz = Szz + mz * mz, Eyz = Syz + my * mz;
+    const double Exxz = Sxx * mz + 2 * Sxz * mx + (mx * mx) * mz;
+    const double Exyz = Sxy * mz + Sxz * my + Syz * mx + mx * my * mz;
+    V[0] = Eyy * (vS + A12) + Exx * (vS - A11) + Exy * (A11 - 2 * vS - A12) +
+           A13 * (Eyz - Exz) + b1 * (mx - my);
+    V[1] = vR * Exx - Exy - Exxz + A21 * Exx + A22 * Exy + A23 * Exz - b2 * mx;
+    V[2] = -Exyz + vB * Ezz - A31 * Exz - A32 * Eyz - A33 * Ezz + b3 * mz;
+}
+
+/* per-component residual second moments of Lorenz 63, Efg = (EX, EY, EZ) (lorenz_63.py:414-432) */
+static void l63_efg_step(const double *th, const double *at, const double *bt,
+                         const double *mt, const double *st, double *E)
+{
+    const double iS1[3] = {1.0, 0.0, 0.0}, iS2[3] = {0.0, 1.0, 0.0}, iS3[3] = {0.0, 0.0, 1.0};
+    double e, Ef[3], Edf[9], dEm[3], dEs[9];
+    /* esde = 0.5 * iS . Efg: unit weights pick the components */
+    l63_step(th, iS1, at, bt, mt, st, &e, Ef, Edf, dEm, dEs); E[0] = 2.0 * e;
+    l63_step(th, iS2, at, bt, mt, st, &e, Ef, Edf, dEm, dEs); E[1] = 2.0 * e;
+    l63_step(th, iS3, at, bt, mt, st, &e, Ef, Edf, dEm, dEs); E[2] = 2.0 * e;
+}
+
+/* m_bar of Lorenz 96: UT mean of the squared residual components (lorenz_96.py:398, 423) */
+static int l96_mbar_step(int D, double theta, const double *at, const double *bt, const double *mt,
+                         const double *st, double *mbar, double *w)
+{
+    const int K = 2 * D + 1;
+    const double kap = 1.05 * D, c = D + kap;
+    const double w0 = kap / c, wi = 1.0 / (2.0 * c);
+    double *cS = w, *L = cS + D * D, *chi = L + D * D, *f = chi + (size_t)K * D;
+    for (int i = 0; i < D * D; ++i) cS[i] = c * st[i];
+    if (chol_lower(D, cS, L)) {
+        memset(cS, 0, sizeof(double) * D * D);
+        for (int i = 0; i < D; ++i) cS[i * D + i] = st[i * D + i];
+        if (chol_lower(D, cS, L)) return 2;
+    }
+    for (int j = 0; j < D; ++j) chi[j] = mt[j];
+    for (int k = 0; k < D; ++k)
+        for (int j = 0; j < D; ++j) {
+            chi[(size_t)(1 + k) * D + j] = mt[j] + L[j * D + k];
+            chi[(size_t)(1 + D + k) * D + j] = mt[j] - L[j * D + k];
+        }
+    const int T = K * D;
+    for (int i = 0; i < T; ++i) {
+        const double fw1 = chi[(i + 1) % T], bw1 = chi[(i - 1 + T) % T], bw2 = chi[(i - 2 + T) % T];
+        f[i] = (fw1 - bw2) * bw1 - chi[i] + theta;
+    }
+    for (int i = 0; i < D; ++i) mbar[i] = 0.0;
+    for (int k = 0; k < K; ++k)
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < D; ++j) s += chi[(size_t)k * D + j] * at[i * D + j];
+            const double rr = f[(size_t)k * D + i] + s - bt[i];
+            mbar[i] += (k == 0 ? w0 : wi) * (rr * rr);
+        }
+    return 0;
+}
+
+int oracle_energy_hyper(const oracle_problem *p, const double *x, const double *mt,
+                        const double *st, double *dth, double *dsig)
+{
+    const int D = p->D, N = p->N, DD = D * D;
+    const double *A = x, *b = x + (size_t)N * DD;
+    if (p->model == MODEL_DW || p->model == MODEL_OU) {
+        double *e = (double *)malloc(sizeof(double) * N), *g = (double *)malloc(sizeof(double) * N);
+        const double th = p->theta[0], sig = p->sigma[0];
+        for (int t = 0; t < N; ++t) {
+            const double mm = mt[t], v = st[t], m2 = mm * mm;
+            const double E2 = m2 + v;
+            if (p->model == MODEL_DW) {
+                const double c = 4.0 * th + A[t], bb = b[t];
+                const double E3 = m2 * mm + 3 * mm * v, E4 = m2 * m2 + 6 * m2 * v + 3 * v * v;
+                const double E6 = m2 * m2 * m2 + 15 * m2 * m2 * v + 45 * m2 * v * v + 15 * v * v * v;
+                e[t] = 8.0 * (E6 - c * E4 + bb * E3) + (c * c * E2) - (2.0 * bb * c * mm) + bb * bb;
+                g[t] = c * E2 - 4.0 * E4 - bb * mm;                       /* :251 */
+            } else {
+                e[t] = E2 * (th - A[t]) * (th - A[t]) + 2.0 * mm * (th - A[t]) * b[t] + b[t] * b[t];
+                g[t] = E2 * (th - A[t]) + mm * b[t];                      /* :223 */
+            }
+        }
+        const double Esde = 0.5 * oracle_trapz(e, N, p->dt_model, p->obs_t, p->M) / sig;
+        const double tz = oracle_trapz(g, N, p->dt_model, p->obs_t, p->M);
+        dth[0] = (p->model == MODEL_DW ? 4.0 * tz : tz) / sig;           /* DW :251-252, OU :223-224 */
+        dsig[0] = -Esde / sig;                                           /* DW :255, OU :227 */
+        free(e); free(g);
+        return 0;
+    }
+    if (p->model != MODEL_L63 && p->model != MODEL_L96) return 1;
+    if (p->model == MODEL_L63 && D != 3) return 1;
+    const int K = 2 * D + 1;
+    double *ft = (double *)malloc(sizeof(double) * (size_t)N * D);   /* per-t theta integrand */
+    double *fs = (double *)malloc(sizeof(double) * (size_t)N * D);   /* per-t sigma integrand */
+    double *w = (double *)malloc(sizeof(double) * ((size_t)2 * DD + (size_t)2 * K * D));
+    double *col = (double *)malloc(sizeof(double) * N);
+    int rc = 0;
+    for (int t = 0; t < N && !rc; ++t) {
+        const double *at = A + (size_t)t * DD, *bt = b + (size_t)t * D, *m = mt + (size_t)t * D,
+                     *S = st + (size_t)t * DD;
+        if (p->model == MODEL_L63) {
+            l63_theta_step(p->theta, at, bt, m, S, ft + (size_t)t * 3);
+            l63_efg_step(p->theta, at, bt, m, S, fs + (size_t)t * 3);
+        } else {
+            rc = l96_mbar_step(D, p->theta[0], at, bt, m, S, fs + (size_t)t * D, w);
+            for (int k = 0; k < D; ++k) {   /* Ef[t] + mt.dot(at.T) - bt  (lorenz_96.py:420) */
+                const int f1 = (k + 1) % D, b1 = (k - 1 + D) % D, b2 = (k - 2 + D) % D;
+                double am = 0.0;
+                for (int j = 0; j < D; ++j) am += m[j] * at[k * D + j];
+                const double Ef = (S[f1 * D + b1] - S[b2 * D + b1]) + (m[f1] - m[b2]) * m[b1] - m[k] + p->theta[0];
+                ft[(size_t)t * D + k] = Ef + am - bt[k];
+            }
+        }
+    }
+    memset(dsig, 0, sizeof(double) * DD);
+    for (int i = 0; i < D && !rc; ++i) {
+        for (int t = 0; t < N; ++t) col[t] = ft[(size_t)t * D + i];
+        dth[i] = (1.0 / p->sigma[i]) * oracle_trapz(col, N, p->dt_model, p->obs_t, p->M);
+        for (int t = 0; t < N; ++t) col[t] = fs[(size_t)t * D + i];
+        /* -0.5 inv_sigma . diag(trapz) . inv_sigma with a diagonal Sigma */
+        dsig[i * D + i] = -0.5 * (1.0 / p->sigma[i]) * oracle_trapz(col, N, p->dt_model, p->obs_t, p->M) *
+                          (1.0 / p->sigma[i]);
+    }
+    free(ft); free(fs); free(w); free(col);
+    return rc;
+}
+
+/* dEobs_dr of GaussianLikelihood.gradients: 1-D (gaussian_like.py:194) at the observation
+ * indices, zero elsewhere; the n-D branch (:226) never fills it (zeros (N, M, M)). */
+void oracle_eobs_dr(const oracle_problem *p, const double *mt, const double *st, double *dr)
+{
+    if (p->D != 1) {
+        memset(dr, 0, sizeof(double) * (size_t)p->N * p->M * p->M);
+        return;
+    }
+    memset(dr, 0, sizeof(double) * p->N);
+    for (int n = 0; n < p->M; ++n) {
+        const long long t = p->obs_t[n];
+        const double y = p->obs_y[n], m = mt[t], Ex2 = m * m + st[t];
+        dr[t] = -0.5 * ((y * y) - 2.0 * y * m + Ex2 + 1.0) / p->R[0];
+    }
+}
+
+/* ------------------------------------------------------------------------ */
 /* observation energy: gaussian_like.py:69-153; jump tables :155-243          */
 /* ------------------------------------------------------------------------ */
 double oracle_eobs(const oracle_problem *p, const double *mt, const double *st)

@@ -55,3 +55,20 @@ def test_oracle_batch_matches_single(oracle):
     for i in range(4):
         Fi, Gi = oracle.eval(prob, X[i])
         assert Fi == F[i] and np.array_equal(Gi, G[i])
+
+
+@pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
+def test_oracle_hyper_gradients(oracle, model):
+    """dEsde_dtheta, dEsde_dsigma (model.energy) and dEobs_dr (GaussianLikelihood.gradients)
+    against the unmodified reference (tests/golden/make_golden_hyper.py)."""
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden"
+    g = np.load(gold / f"eval_{model}_rk2.npz")
+    h = np.load(gold / f"hyper_{model}.npz")
+    prob = Problem.from_golden(g)
+    dth, dsig = oracle.energy_hyper(prob, g["x"], g["mt"], g["st"])
+    assert rel_err(dth, h["dEsde_dtheta"]) < TOL
+    assert rel_err(dsig, h["dEsde_dsigma"]) < TOL
+    dr = oracle.eobs_dr(prob, g["mt"], g["st"])
+    assert dr.shape == h["dEobs_dr"].shape
+    assert rel_err(dr, h["dEobs_dr"]) < TOL if np.abs(h["dEobs_dr"]).max() > 0 else not dr.any()

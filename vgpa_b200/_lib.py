@@ -69,9 +69,9 @@ def _load():
     lib.vgpa_solve_bwd.restype = C.c_int
     lib.vgpa_solve_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 7
     lib.vgpa_model_energy.restype = C.c_int
-    lib.vgpa_model_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 11
+    lib.vgpa_model_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 13
     lib.vgpa_obs_energy.restype = C.c_int
-    lib.vgpa_obs_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip] + [_dp] * 7
+    lib.vgpa_obs_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip] + [_dp] * 8
     lib.vgpa_host_alloc.restype = C.c_void_p
     lib.vgpa_host_alloc.argtypes = [C.c_int64]
     lib.vgpa_host_free.restype = None

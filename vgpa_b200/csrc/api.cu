@@ -642,7 +642,7 @@ int vgpa_solve_bwd(int device, int method, int D, int N, double dt, const double
 
 int vgpa_model_energy(int device, int model, int D, int N, double dt_model, const double* theta,
                       const double* sigma, const double* A, const double* b, const double* m, const double* S,
-                      double* Esde, double* Ef, double* Edf, double* dEm, double* dEs)
+                      double* Esde, double* Ef, double* Edf, double* dEm, double* dEs, double* dEth, double* dEsig)
 {
     if (model < 0 || model > 3) { g_create_error = "Unknown stochastic model"; return VGPA_EINVAL; }
     const int needD = (model == VGPA_MODEL_L63) ? 3 : (model == VGPA_MODEL_L96 ? 40 : 1);
@@ -654,11 +654,15 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
     if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
     const long long nv = (long long)N * D, nm = (long long)N * D * D;
     const int nth = n_theta(model);
-    DevBuf dx, dth, dsig, dmt, dst, dgm, dgs, des, def, dedf, dparts, dzero, dF, dstat;
+    DevBuf dx, dth, dsig, dmt, dst, dgm, dgs, des, def, dedf, dparts, dzero, dF, dstat, dft, dfs, dhth, dhsig;
     auto cleanup = [&]() {
-        for (DevBuf* q : {&dx, &dth, &dsig, &dmt, &dst, &dgm, &dgs, &des, &def, &dedf, &dparts, &dzero, &dF, &dstat})
+        for (DevBuf* q : {&dx, &dth, &dsig, &dmt, &dst, &dgm, &dgs, &des, &def, &dedf, &dparts, &dzero, &dF, &dstat,
+                          &dft, &dfs, &dhth, &dhsig})
             q->release();
     };
+    const bool hyper = (dEth != nullptr) || (dEsig != nullptr);
+    const int nhth = (model == VGPA_MODEL_L96) ? D : nth;   // lorenz_96.py:431: one entry per state dimension
+    const long long nsig = (D == 1) ? 1 : (long long)D * D;
     cudaError_t e;
     if ((e = dx.alloc(sizeof(double) * (nm + nv))) != cudaSuccess || (e = dth.alloc(sizeof(double) * nth)) != cudaSuccess ||
         (e = dsig.alloc(sizeof(double) * D)) != cudaSuccess || (e = dmt.alloc(sizeof(double) * nv)) != cudaSuccess ||
@@ -691,12 +695,26 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
     if (model == VGPA_MODEL_L96) launch_l96_energy(bt, sc, dx.as<double>(), 0, 0, 1, ex, nullptr);
     else launch_small_energy(bt, sc, dx.as<double>(), 0, 0, 1, ex, nullptr);
     launch_finalize(bt, sc, dF.as<double>(), 0, 1, ex, nullptr);
+    if (hyper) {
+        if ((e = dft.alloc(sizeof(double) * (size_t)N * nhth)) != cudaSuccess || (e = dfs.alloc(sizeof(double) * nv)) != cudaSuccess ||
+            (e = dhth.alloc(sizeof(double) * nhth)) != cudaSuccess || (e = dhsig.alloc(sizeof(double) * nsig)) != cudaSuccess) {
+            cleanup();
+            g_create_error = std::string("CUDA error in vgpa_model_energy: ") + cudaGetErrorString(e);
+            return VGPA_ECUDA;
+        }
+        // parts[1] = Esde (written by finalize on the same stream)
+        launch_hyper(model, D, N, dt_model, dth.as<double>(), dsig.as<double>(), dx.as<double>(), dmt.as<double>(),
+                     dst.as<double>(), dparts.as<double>() + 1, dft.as<double>(), dfs.as<double>(),
+                     dhth.as<double>(), dhsig.as<double>(), dstat.as<int>(), nullptr);
+    }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     double parts[3] = {0, 0, 0};
     int stat = 0;
     if (e == cudaSuccess) e = cudaMemcpy(parts, dparts.p, sizeof parts, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(&stat, dstat.p, sizeof stat, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dEth) e = cudaMemcpy(dEth, dhth.p, sizeof(double) * nhth, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dEsig) e = cudaMemcpy(dEsig, dhsig.p, sizeof(double) * nsig, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(Ef, def.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(Edf, dedf.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(dEm, dgm.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
@@ -717,7 +735,7 @@ int vgpa_model_energy(int device, int model, int D, int N, double dt_model, cons
 }
 
 int vgpa_obs_energy(int device, int D, int N, int M, const int64_t* obs_t, const double* obs_y, const double* R,
-                    const double* mt, const double* st, double* Eobs, double* jm, double* js)
+                    const double* mt, const double* st, double* Eobs, double* jm, double* js, double* dr)
 {
     if ((D != 1 && D != 3 && D != 40) || N < 2 || M < 0 || M > N) { g_create_error = "Wrong dimensions for the likelihood"; return VGPA_EINVAL; }
     if ((M > 0 && (!obs_t || !obs_y)) || !R || !mt || !st || !Eobs || !jm || !js) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
@@ -725,8 +743,8 @@ int vgpa_obs_energy(int device, int D, int N, int M, const int64_t* obs_t, const
         if (obs_t[n] < 0 || obs_t[n] >= N) { g_create_error = "observation index out of range"; return VGPA_EINVAL; }
     if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
     const long long nv = (long long)N * D, nm = (long long)N * D * D;
-    DevBuf dot, doy, dR, dmt, dst, djm, djs, des, dparts, dzero, dF;
-    auto cleanup = [&]() { for (DevBuf* q : {&dot, &doy, &dR, &dmt, &dst, &djm, &djs, &des, &dparts, &dzero, &dF}) q->release(); };
+    DevBuf dot, doy, dR, dmt, dst, djm, djs, des, dparts, dzero, dF, ddr;
+    auto cleanup = [&]() { for (DevBuf* q : {&dot, &doy, &dR, &dmt, &dst, &djm, &djs, &des, &dparts, &dzero, &dF, &ddr}) q->release(); };
     std::vector<long long> ot(std::max(M, 1), 0);
     for (int n = 0; n < M; ++n) ot[n] = obs_t[n];
     cudaError_t e;
@@ -758,10 +776,23 @@ int vgpa_obs_energy(int device, int D, int N, int M, const int64_t* obs_t, const
     launch_finalize(bt, sc, dF.as<double>(), 0, 1, ex, nullptr);
     launch_jump_tables(D, N, M, dot.as<long long>(), doy.as<double>(), dR.as<double>(), dmt.as<double>(),
                        djm.as<double>(), djs.as<double>(), nullptr);
+    if (dr != nullptr && D == 1) {
+        if ((e = ddr.alloc(sizeof(double) * N)) != cudaSuccess) {
+            cleanup();
+            g_create_error = std::string("CUDA error in vgpa_obs_energy: ") + cudaGetErrorString(e);
+            return VGPA_ECUDA;
+        }
+        launch_obs_dr(N, M, dot.as<long long>(), doy.as<double>(), dR.as<double>(), dmt.as<double>(), dst.as<double>(),
+                      ddr.as<double>(), nullptr);
+    }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     double parts[3] = {0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpy(parts, dparts.p, sizeof parts, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dr != nullptr) {
+        if (D == 1) e = cudaMemcpy(dr, ddr.p, sizeof(double) * N, cudaMemcpyDeviceToHost);
+        else std::fill(dr, dr + (size_t)N * M * M, 0.0);   // the reference's n-D branch returns zeros (gaussian_like.py:226)
+    }
     if (e == cudaSuccess) e = cudaMemcpy(jm, djm.p, sizeof(double) * nv, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(js, djs.p, sizeof(double) * nm, cudaMemcpyDeviceToHost);
     cleanup();

@@ -90,6 +90,14 @@ void launch_bwd_dense(int method, int D, int N, double dt, const double* A, cons
                       const double* dEs, const double* jm, const double* js, double* lam,
                       double* psi, cudaStream_t st);
 
+// Hyper-parameter gradients of model.energy (hyper.cu); all pointers are device pointers.
+void launch_hyper(int model, int D, int N, double dt_model, const double* theta, const double* sigma,
+                  const double* x, const double* mt, const double* st, const double* esde, double* ft,
+                  double* fs, double* dth, double* dsig, int* status, cudaStream_t stream);
+// dEobs_dr of the 1-D likelihood (N values, zero except at obs_t).
+void launch_obs_dr(int N, int M, const long long* obs_t, const double* obs_y, const double* R,
+                   const double* mt, const double* st, double* dr, cudaStream_t stream);
+
 // Dense jump tables dEobs_dm (N,D), dEobs_ds (N,D,D) (GaussianLikelihood.gradients).
 void launch_jump_tables(int D, int N, int M, const long long* obs_t, const double* obs_y, const double* R,
                         const double* mt, double* jm, double* js, cudaStream_t st);

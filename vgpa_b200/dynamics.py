@@ -101,12 +101,13 @@ class StochasticProcess(object):
         return np.atleast_1d(s)
 
     def energy(self, linear_a, offset_b, m, s, obs_t):
-        """model.energy: returns Esde, (Ef, Edf), (dEsde_dm, dEsde_ds, dEsde_dtheta, dEsde_dsigma).
-        The two hyper-parameter gradients are discarded by VarGP (variational.py:175)
-        and are returned as None."""
-        Esde, Ef, Edf, dm, ds = engine.model_energy(self.model_key, self.theta, self._sigma_diag(),
-                                                    linear_a, offset_b, m, s, float(self.time_step))
-        return Esde, (Ef, Edf), (dm, ds, None, None)
+        """model.energy: returns Esde, (Ef, Edf), (dEsde_dm, dEsde_ds, dEsde_dtheta, dEsde_dsigma),
+        all computed on the GPU.  (VarGP's hot path does not come through here: it never needs the
+        two hyper-parameter gradients, which the reference computes and discards, variational.py:175.)"""
+        Esde, Ef, Edf, dm, ds, dth, dsig = engine.model_energy(self.model_key, self.theta, self._sigma_diag(),
+                                                               linear_a, offset_b, m, s, float(self.time_step),
+                                                               hyper=True)
+        return Esde, (Ef, Edf), (dm, ds, dth, dsig)
 
 
 class _Scalar1D(StochasticProcess):

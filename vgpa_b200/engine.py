@@ -201,9 +201,9 @@ def solve_bwd(method, A, dEsde_dm, dEsde_ds, dEobs_dm, dEobs_ds, dt, device=0):
     return (lam, psi) if single else (lam.reshape(N, D), psi.reshape(N, D, D))
 
 
-def model_energy(model, theta, sigma_diag, A, b, m, S, dt_model, device=0):
+def model_energy(model, theta, sigma_diag, A, b, m, S, dt_model, device=0, hyper=False):
     """model.energy(A, b, m, S, obs_t) of the reference's StochasticProcess classes.
-    Returns Esde, Ef, Edf, dEsde_dm, dEsde_ds."""
+    Returns Esde, Ef, Edf, dEsde_dm, dEsde_ds (+ dEsde_dtheta, dEsde_dsigma with hyper=True)."""
     key = str(model).upper()
     D = MODEL_DIM[key]
     b = f64(b)
@@ -214,16 +214,22 @@ def model_energy(model, theta, sigma_diag, A, b, m, S, dt_model, device=0):
         raise ValueError("model_energy: inconsistent shapes")
     Esde = np.zeros(1)
     Ef, Edf, dm, ds = np.empty(N * D), np.empty(N * D * D), np.empty(N * D), np.empty(N * D * D)
+    nth = {"DW": 1, "OU": 1, "L63": 3, "L96": D}[key]
+    dth = np.zeros(nth) if hyper else None
+    dsig = np.zeros(1 if D == 1 else D * D) if hyper else None
     rc = lib.vgpa_model_energy(device, MODELS[key], D, N, float(dt_model), dptr(th), dptr(sg), dptr(A),
-                               dptr(b), dptr(m), dptr(S), dptr(Esde), dptr(Ef), dptr(Edf), dptr(dm), dptr(ds))
+                               dptr(b), dptr(m), dptr(S), dptr(Esde), dptr(Ef), dptr(Edf), dptr(dm), dptr(ds),
+                               dptr(dth) if hyper else None, dptr(dsig) if hyper else None)
     raise_for(rc, None)
     if D == 1:
-        return float(Esde[0]), Ef, Edf, dm, ds
-    return float(Esde[0]), Ef.reshape(N, D), Edf.reshape(N, D, D), dm.reshape(N, D), ds.reshape(N, D, D)
+        out = (float(Esde[0]), Ef, Edf, dm, ds)
+        return out + (float(dth[0]), float(dsig[0])) if hyper else out
+    out = (float(Esde[0]), Ef.reshape(N, D), Edf.reshape(N, D, D), dm.reshape(N, D), ds.reshape(N, D, D))
+    return out + (dth, dsig.reshape(D, D)) if hyper else out
 
 
-def obs_energy(obs_t, obs_y, R_diag, m, s, device=0):
-    """GaussianLikelihood.__call__ / .gradients: returns Eobs, dEobs_dm, dEobs_ds."""
+def obs_energy(obs_t, obs_y, R_diag, m, s, device=0, with_dr=False):
+    """GaussianLikelihood.__call__ / .gradients: returns Eobs, dEobs_dm, dEobs_ds (+ dEobs_dr)."""
     m = f64(m)
     single = m.ndim == 1
     N = m.shape[0]
@@ -235,9 +241,12 @@ def obs_energy(obs_t, obs_y, R_diag, m, s, device=0):
         raise ValueError("obs_energy: inconsistent shapes")
     E = np.zeros(1)
     jm, js = np.empty(N * D), np.empty(N * D * D)
+    dr = np.empty(N if single else N * M * M) if with_dr else None
     rc = lib.vgpa_obs_energy(device, D, N, M, ot.ctypes.data_as(C.POINTER(C.c_int64)), dptr(oy), dptr(R),
-                             dptr(m), dptr(s), dptr(E), dptr(jm), dptr(js))
+                             dptr(m), dptr(s), dptr(E), dptr(jm), dptr(js), dptr(dr) if with_dr else None)
     raise_for(rc, None)
     if single:
-        return float(E[0]), jm, js
-    return float(E[0]), jm.reshape(N, D), js.reshape(N, D, D)
+        out = (float(E[0]), jm, js)
+        return out + (dr,) if with_dr else out
+    out = (float(E[0]), jm.reshape(N, D), js.reshape(N, D, D))
+    return out + (dr.reshape(N, M, M),) if with_dr else out

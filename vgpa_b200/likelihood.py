@@ -54,10 +54,11 @@ class GaussianLikelihood(object):
         return engine.obs_energy(self.obs_t, self.obs_v, self.noise_diag(), m, s, self.device)[0]
 
     def gradients(self, m, s=None):
-        """dEobs_dm, dEobs_ds, dEobs_dr (gaussian_like.py:155-243); dEobs_dr is not on
-        the path (variational.py:178 discards it) and is returned as None."""
+        """dEobs_dm, dEobs_ds, dEobs_dr (gaussian_like.py:155-243).  As in the reference, the 1-D
+        dEobs_dr needs the marginal variances s; the n-D one is all zeros of shape (N, M, M)."""
         m = np.asarray(m, dtype=float)
         if s is None:
             s = np.zeros(m.shape + (() if m.ndim == 1 else (m.shape[1],)))
-        _, jm, js = engine.obs_energy(self.obs_t, self.obs_v, self.noise_diag(), m, s, self.device)
-        return jm, js, None
+        _, jm, js, dr = engine.obs_energy(self.obs_t, self.obs_v, self.noise_diag(), m, s, self.device,
+                                          with_dr=True)
+        return jm, js, dr
