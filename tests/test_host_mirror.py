@@ -109,3 +109,21 @@ def test_reference_style_errors():
         DoubleWell(0.8, 1.0).sample_path
     with pytest.raises(ValueError):
         Simulation("x").setup({**mg.config("DW", "euler"), "Model": "nope"})
+
+
+@pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
+def test_prior_kl0_gradients_match_reference(model):
+    """PriorKL0.gradients (prior_kl0.py:94-175) against the unmodified reference (hyper_*.npz)."""
+    from pathlib import Path
+    from vgpa_b200.prior import PriorKL0
+    gold = Path(__file__).resolve().parent / "golden"
+    g = np.load(gold / f"eval_{model}_rk2.npz")
+    h = np.load(gold / f"hyper_{model}.npz")
+    if int(g["D"]) == 1:
+        kl0 = PriorKL0(float(g["mu0"]), float(g["tau0"]), True)
+        dm, ds = kl0.gradients(float(g["m0"]), float(g["s0"]), g["lamt"][0], g["psit"][0])
+    else:
+        kl0 = PriorKL0(g["mu0"], g["tau0"], False)
+        dm, ds = kl0.gradients(g["m0"], g["s0"], g["lamt"][0], g["psit"][0])
+    assert np.allclose(dm, h["dKL0_dm0"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(ds, h["dKL0_ds0"], rtol=1e-12, atol=1e-14)

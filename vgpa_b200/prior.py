@@ -35,3 +35,12 @@ class PriorKL0(object):
         z0 = m0 - self.mu0
         return 0.5 * (_log_det(self.tau0.dot(_chol_inv(s0))) +
                       np.sum(np.diag(_chol_inv(self.tau0).dot(z0.T.dot(z0) + s0 - self.tau0))))
+
+    def gradients(self, m0, s0, lam0, psi0):
+        """dKL0/dm0, dKL0/ds0 (prior_kl0.py:94-175): host arithmetic on the t = 0 Lagrange multipliers
+        (`VarGP.arg_out["lamt"][0]`, `["psit"][0]`); like __call__ it is not on the per-iteration path."""
+        z0 = m0 - self.mu0
+        if self.single_dim:
+            return lam0 + z0 / self.tau0, psi0 + 0.5 * (1.0 / self.tau0 - 1.0 / s0)
+        return (lam0 + np.linalg.solve(self.tau0, z0.T).T,
+                psi0 + 0.5 * (_chol_inv(self.tau0) - _chol_inv(s0)))
