@@ -56,8 +56,8 @@ def main():
         _, _, dr = lik.gradients(g["mt"], g["st"])
         # PriorKL0.gradients (prior_kl0.py:94-175) at the t = 0 multipliers of the same evaluation
         if D == 1:
-            kl0 = PriorKL0(float(g["mu0"]), float(g["tau0"]), True)
-            dk_m, dk_s = kl0.gradients(float(g["m0"]), float(g["s0"]), g["lamt"][0], g["psit"][0])
+            kl0 = PriorKL0(float(np.ravel(g["mu0"])[0]), float(np.ravel(g["tau0"])[0]), True)
+            dk_m, dk_s = kl0.gradients(float(np.ravel(g["m0"])[0]), float(np.ravel(g["s0"])[0]), g["lamt"][0], g["psit"][0])
         else:
             kl0 = PriorKL0(g["mu0"], g["tau0"], False)
             dk_m, dk_s = kl0.gradients(g["m0"], g["s0"], g["lamt"][0], g["psit"][0])

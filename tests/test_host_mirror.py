@@ -120,8 +120,8 @@ def test_prior_kl0_gradients_match_reference(model):
     g = np.load(gold / f"eval_{model}_rk2.npz")
     h = np.load(gold / f"hyper_{model}.npz")
     if int(g["D"]) == 1:
-        kl0 = PriorKL0(float(g["mu0"]), float(g["tau0"]), True)
-        dm, ds = kl0.gradients(float(g["m0"]), float(g["s0"]), g["lamt"][0], g["psit"][0])
+        kl0 = PriorKL0(float(np.ravel(g["mu0"])[0]), float(np.ravel(g["tau0"])[0]), True)
+        dm, ds = kl0.gradients(float(np.ravel(g["m0"])[0]), float(np.ravel(g["s0"])[0]), g["lamt"][0], g["psit"][0])
     else:
         kl0 = PriorKL0(g["mu0"], g["tau0"], False)
         dm, ds = kl0.gradients(g["m0"], g["s0"], g["lamt"][0], g["psit"][0])
