@@ -168,6 +168,15 @@ int vgpa_obs_energy(int device, int D, int N, int M, const int64_t *obs_t, const
 /* dEobs_dr (may be NULL): third output of GaussianLikelihood.gradients -- N values for D = 1
  * (gaussian_like.py:194), N x M x M zeros for D > 1 (the reference never fills it, :226). */
 
+/* VarGP.initialization (variational.py:73-139) for every problem of the handle: the starting
+ * point x0 = [A0 | b0] from cubic splines (scipy CubicSpline, not-a-knot) through each problem's
+ * observations, written to DEVICE rows d_x + p * x_stride on `stream` (asynchronous), or to HOST
+ * rows (vgpa_initialization_host, synchronous).  t0 = first point of the time window; the grid
+ * is t0 + k * dt_model.  VGPA_EINVAL when an observation sits at the first or last grid index
+ * (the reference's CubicSpline raises: knots must be strictly increasing) or M < 1. */
+int vgpa_initialization(vgpa_handle *h, double t0, double *d_x, int64_t x_stride, void *stream);
+int vgpa_initialization_host(vgpa_handle *h, double t0, double *x, int64_t x_stride);
+
 /* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
 void *vgpa_host_alloc(int64_t bytes);
 void vgpa_host_free(void *p);

@@ -133,6 +133,8 @@ class Oracle:
         L.oracle_bwd.argtypes = [C.POINTER(_CProblem)] + [_dp] * 7
         L.oracle_energy.restype = C.c_int
         L.oracle_energy.argtypes = [C.POINTER(_CProblem)] + [_dp] * 9
+        L.oracle_initialization.restype = C.c_int
+        L.oracle_initialization.argtypes = [C.POINTER(_CProblem), C.c_double, _dp]
         L.oracle_energy_hyper.restype = C.c_int
         L.oracle_energy_hyper.argtypes = [C.POINTER(_CProblem)] + [_dp] * 5
         L.oracle_eobs_dr.restype = None
@@ -179,6 +181,13 @@ class Oracle:
             outs[k] = outs[k].reshape(shp_m if k in ("st", "psit", "Edf", "dEsde_ds") else shp_v)
         outs.update(F=float(F[0]), E0=parts[0], Esde=parts[1], Eobs=parts[2], grad=grad)
         return outs
+
+    def initialization(self, prob, t0=0.0):
+        """VarGP.initialization: x0 = [A0 | b0]."""
+        x0 = np.zeros(prob.N * prob.D * (prob.D + 1))
+        cp = prob.c_struct()
+        self._raise(self.lib.oracle_initialization(C.byref(cp), float(t0), _p(x0)))
+        return x0
 
     def energy_hyper(self, prob, x, mt, st):
         """dEsde_dtheta, dEsde_dsigma of model.energy (reference shapes)."""

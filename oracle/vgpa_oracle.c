@@ -863,6 +863,113 @@ void oracle_eobs_dr(const oracle_problem *p, const double *mt, const double *st,
 }
 
 /* ------------------------------------------------------------------------ */
+/* VarGP.initialization (variational.py:73-139): x0 = [A0 | b0] from a cubic    */
+/* spline through the observations, each dimension separately.  The spline is  */
+/* scipy.interpolate.CubicSpline with its default 'not-a-knot' ends (scipy is   */
+/* an unpinned dependency of the reference, requirements.txt; 1.18.1 in the     */
+/* authoring container): first derivatives s at the knots from the tridiagonal  */
+/* system of CubicSpline.__init__ (n >= 4), the parabola special case (n = 3),  */
+/* the straight line (n = 2); then the Hermite cubic of CubicHermiteSpline,     */
+/* evaluated as c3 + c2 d + c1 d^2 + c0 d^3.  tw[k] = t0 + k * dt_model.        */
+/* ------------------------------------------------------------------------ */
+static int spline_slopes(int n, const double *x, const double *y, double *s, double *w /* 2 n */)
+{
+    if (n < 2) return 1;
+    for (int i = 0; i + 1 < n; ++i)
+        if (!(x[i + 1] > x[i])) return 1;                       /* scipy: x must be strictly increasing */
+    if (n == 2) { s[0] = s[1] = (y[1] - y[0]) / (x[1] - x[0]); return 0; }
+    if (n == 3) { /* parabola through the three points: 3 x 3 system */
+        const double dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+        const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
+        /* [1 1 0; dx1 2(dx0+dx1) dx0; 0 1 1] s = [2 sl0; 3(dx0 sl1 + dx1 sl0); 2 sl1] */
+        const double b0 = 2 * sl0, b1 = 3 * (dx0 * sl1 + dx1 * sl0), b2 = 2 * sl1;
+        /* s0 = b0 - s1, s2 = b2 - s1  =>  dx1 (b0 - s1) + 2 (dx0 + dx1) s1 + dx0 (b2 - s1) = b1 */
+        const double s1 = (b1 - dx1 * b0 - dx0 * b2) / (dx0 + dx1);
+        s[0] = b0 - s1; s[1] = s1; s[2] = b2 - s1;
+        return 0;
+    }
+    /* tridiagonal system, Thomas algorithm: w[0..n) modified upper diagonal, s = modified rhs */
+    double *cp = w;
+    {
+        const double dx0 = x[1] - x[0], dx1 = x[2] - x[1], d = x[2] - x[0];
+        const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
+        const double diag = dx1, up = d;
+        const double rhs = ((dx0 + 2 * d) * dx1 * sl0 + dx0 * dx0 * sl1) / d;
+        cp[0] = up / diag;
+        s[0] = rhs / diag;
+    }
+    for (int i = 1; i < n - 1; ++i) {
+        const double dxm = x[i] - x[i - 1], dxp = x[i + 1] - x[i];
+        const double slm = (y[i] - y[i - 1]) / dxm, slp = (y[i + 1] - y[i]) / dxp;
+        const double lo = dxp, diag = 2 * (dxm + dxp), up = dxm;
+        const double rhs = 3 * (dxp * slm + dxm * slp);
+        const double den = diag - lo * cp[i - 1];
+        cp[i] = up / den;
+        s[i] = (rhs - lo * s[i - 1]) / den;
+    }
+    {
+        const int i = n - 1;
+        const double dxm = x[i] - x[i - 1], dxmm = x[i - 1] - x[i - 2], d = x[i] - x[i - 2];
+        const double slm = (y[i] - y[i - 1]) / dxm, slmm = (y[i - 1] - y[i - 2]) / dxmm;
+        const double lo = d, diag = dxmm;
+        const double rhs = (dxm * dxm * slmm + (2 * d + dxm) * dxmm * slm) / d;
+        const double den = diag - lo * cp[i - 1];
+        s[i] = (rhs - lo * s[i - 1]) / den;
+    }
+    for (int i = n - 2; i >= 0; --i) s[i] -= cp[i] * s[i + 1];
+    return 0;
+}
+
+static double spline_eval(int n, const double *x, const double *y, const double *s, double t)
+{
+    int i = 0;                                   /* interval: x[i] <= t < x[i+1], last one closed */
+    while (i < n - 2 && t >= x[i + 1]) ++i;
+    const double h = x[i + 1] - x[i], slope = (y[i + 1] - y[i]) / h;
+    const double tt = (s[i] + s[i + 1] - 2 * slope) / h;
+    const double c0 = tt / h, c1 = (slope - s[i]) / h - tt, c2 = s[i], c3 = y[i];
+    const double d = t - x[i];
+    return c3 + c2 * d + c1 * (d * d) + c0 * (d * d * d);
+}
+
+int oracle_initialization(const oracle_problem *p, double t0, double *x0)
+{
+    const int D = p->D, N = p->N, M = p->M, n = M + 2, DD = D * D;
+    if (M < 1) return 1;
+    double *x = (double *)malloc(sizeof(double) * n), *y = (double *)malloc(sizeof(double) * n);
+    double *s = (double *)malloc(sizeof(double) * n), *w = (double *)malloc(sizeof(double) * 2 * n);
+    double *mt0 = (double *)malloc(sizeof(double) * (size_t)N * D);
+    double *a0 = x0, *b0 = x0 + (size_t)N * DD;
+    int rc = 0;
+    x[0] = t0;                                                /* time_x (:86) */
+    for (int j = 0; j < M; ++j) x[1 + j] = t0 + (double)p->obs_t[j] * p->dt_model;
+    x[n - 1] = t0 + (double)(N - 1) * p->dt_model;
+    for (int d = 0; d < D && !rc; ++d) {
+        y[0] = p->obs_y[d];                                   /* obs_z (:91 / :104) */
+        for (int j = 0; j < M; ++j) y[1 + j] = p->obs_y[(size_t)j * D + d];
+        y[n - 1] = p->obs_y[(size_t)(M - 1) * D + d];
+        rc = spline_slopes(n, x, y, s, w);
+        for (int k = 0; k < N && !rc; ++k)
+            mt0[(size_t)k * D + d] = spline_eval(n, x, y, s, t0 + (double)k * p->dt_model);
+    }
+    if (!rc) {
+        if (D == 1) {                                         /* :94-101 */
+            for (int k = 0; k < N; ++k) { a0[k] = 0.5 * (p->sigma[0] / 0.25) * 1.0; b0[k] = mt0[k]; }
+        } else {                                              /* :103-133 */
+            memset(a0, 0, sizeof(double) * (size_t)N * DD);
+            for (int k = 0; k < N; ++k)
+                for (int d = 0; d < D; ++d) {
+                    const double ad = 0.5 * (p->sigma[d] / 0.25);
+                    a0[(size_t)k * DD + d * D + d] = ad;
+                    const double m0 = mt0[(size_t)k * D + d];
+                    b0[(size_t)k * D + d] = (k < N - 1) ? (mt0[(size_t)(k + 1) * D + d] - m0) / p->dt_model + ad * m0 : ad * m0; /* self.dt = model.time_step (:57) */
+                }
+        }
+    }
+    free(x); free(y); free(s); free(w); free(mt0);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------ */
 /* observation energy: gaussian_like.py:69-153; jump tables :155-243          */
 /* ------------------------------------------------------------------------ */
 double oracle_eobs(const oracle_problem *p, const double *mt, const double *st)

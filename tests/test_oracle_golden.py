@@ -72,3 +72,13 @@ def test_oracle_hyper_gradients(oracle, model):
     dr = oracle.eobs_dr(prob, g["mt"], g["st"])
     assert dr.shape == h["dEobs_dr"].shape
     assert rel_err(dr, h["dEobs_dr"]) < TOL if np.abs(h["dEobs_dr"]).max() > 0 else not dr.any()
+
+
+@pytest.mark.parametrize("path", golden_eval_files(), ids=lambda p: p.split("eval_")[-1][:-4])
+def test_oracle_initialization_reproduces_reference(oracle, path):
+    """VarGP.initialization (cubic splines through the observations) against the x0 the unmodified
+    reference produced (goldens: key x0)."""
+    g = np.load(path)
+    prob = Problem.from_golden(g)
+    x0 = oracle.initialization(prob, 0.0)
+    assert rel_err(x0, g["x0"]) < TOL

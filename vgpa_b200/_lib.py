@@ -60,6 +60,10 @@ def _load():
     lib.vgpa_eval_device.restype = C.c_int
     lib.vgpa_eval_device.argtypes = [H, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_void_p]
+    lib.vgpa_initialization.restype = C.c_int
+    lib.vgpa_initialization.argtypes = [H, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.vgpa_initialization_host.restype = C.c_int
+    lib.vgpa_initialization_host.argtypes = [H, C.c_double, _dp, C.c_int64]
     lib.vgpa_sync.restype = C.c_int
     lib.vgpa_sync.argtypes = [H]
     lib.vgpa_eval_full.restype = C.c_int

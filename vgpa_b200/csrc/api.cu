@@ -804,6 +804,76 @@ int vgpa_obs_energy(int device, int D, int N, int M, const int64_t* obs_t, const
     return VGPA_OK;
 }
 
+static int init_check(vgpa_handle* h, const double* x, int64_t x_stride)
+{
+    if (x == nullptr) return h->fail(VGPA_EINVAL, "x is NULL");
+    if (x_stride < h->n_x) return h->fail(VGPA_EINVAL, "x_stride %lld < %lld", (long long)x_stride, h->n_x);
+    if (h->d.M < 1) return h->fail(VGPA_EINVAL, "initialization needs at least one observation");
+    return VGPA_OK;
+}
+
+int vgpa_initialization(vgpa_handle* h, double t0, double* d_x, int64_t x_stride, void* stream)
+{
+    if (!h) return VGPA_EINVAL;
+    if (int rc = init_check(h, d_x, x_stride)) return rc;
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = h->d.B, D = h->d.D, n = h->d.M + 2;
+    DevBuf scratch, err;
+    cudaError_t e;
+    if ((e = scratch.alloc(sizeof(double) * (size_t)B * D * 2 * n)) != cudaSuccess || (e = err.alloc(sizeof(int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(err.p, 0, sizeof(int), st)) != cudaSuccess) {
+        scratch.release(); err.release();
+        return h->cuda_fail(e, "vgpa_initialization");
+    }
+    launch_initialization(h->batch, 0, B, t0, scratch.as<double>(), d_x, x_stride, err.as<int>(), st);
+    h->launches += 2;
+    int bad = 0;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, err.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the scratch is released below
+    scratch.release(); err.release();
+    if (e != cudaSuccess) return h->cuda_fail(e, "vgpa_initialization");
+    if (bad) return h->fail(VGPA_EINVAL, "`x` must be strictly increasing sequence: an observation sits at the first or last grid index");
+    return VGPA_OK;
+}
+
+int vgpa_initialization_host(vgpa_handle* h, double t0, double* x, int64_t x_stride)
+{
+    if (!h) return VGPA_EINVAL;
+    if (int rc = init_check(h, x, x_stride)) return rc;
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    const int B = h->d.B, D = h->d.D, n = h->d.M + 2;
+    const long long nx = h->n_x;
+    const int C = std::max(1, std::min(B, 64));
+    DevBuf scratch, err, dx;
+    auto cleanup = [&]() { scratch.release(); err.release(); dx.release(); };
+    cudaError_t e;
+    if ((e = scratch.alloc(sizeof(double) * (size_t)C * D * 2 * n)) != cudaSuccess || (e = err.alloc(sizeof(int))) != cudaSuccess ||
+        (e = dx.alloc(sizeof(double) * (size_t)C * nx)) != cudaSuccess || (e = cudaMemset(err.p, 0, sizeof(int))) != cudaSuccess) {
+        cleanup();
+        return h->cuda_fail(e, "vgpa_initialization_host");
+    }
+    for (int p0 = 0; p0 < B && e == cudaSuccess; p0 += C) {
+        const int count = std::min(C, B - p0);
+        // kernels index problems globally: offset the staging pointer accordingly
+        launch_initialization(h->batch, p0, count, t0, scratch.as<double>(), dx.as<double>() - (long long)p0 * nx, nx,
+                              err.as<int>(), h->s_comp);
+        h->launches += 2;
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(x + (long long)p0 * x_stride, sizeof(double) * x_stride, dx.p, sizeof(double) * nx,
+                                  sizeof(double) * nx, count, cudaMemcpyDeviceToHost, h->s_comp);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_comp);
+    }
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, err.p, sizeof(int), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return h->cuda_fail(e, "vgpa_initialization_host");
+    if (bad) return h->fail(VGPA_EINVAL, "`x` must be strictly increasing sequence: an observation sits at the first or last grid index");
+    return VGPA_OK;
+}
+
 void* vgpa_host_alloc(int64_t bytes)
 {
     void* p = nullptr;

@@ -90,6 +90,10 @@ void launch_bwd_dense(int method, int D, int N, double dt, const double* A, cons
                       const double* dEs, const double* jm, const double* js, double* lam,
                       double* psi, cudaStream_t st);
 
+// VarGP.initialization for problems p0 .. p0 + count - 1 (init.cu); scratch: count * D * 2 (M + 2) doubles.
+void launch_initialization(const Batch& b, int p0, int count, double t0, double* scratch, double* x,
+                           long long x_stride, int* err, cudaStream_t st);
+
 // Hyper-parameter gradients of model.energy (hyper.cu); all pointers are device pointers.
 void launch_hyper(int model, int D, int N, double dt_model, const double* theta, const double* sigma,
                   const double* x, const double* mt, const double* st, const double* esde, double* ft,

@@ -123,6 +123,18 @@ class BatchEvaluator:
     def sync(self):
         raise_for(lib.vgpa_sync(self._h), self._h)
 
+    def initialization(self, t0=0.0):
+        """VarGP.initialization for every problem of the batch, computed on the GPU: (B, n_x) host array."""
+        X = np.empty((self.B, self.n_x))
+        raise_for(lib.vgpa_initialization_host(self._h, float(t0), dptr(X), self.n_x), self._h)
+        return X
+
+    def initialization_device(self, x_ptr, x_stride=None, t0=0.0, stream=0):
+        """The same into DEVICE rows x_ptr + p * x_stride (an ensemble's starting points never leave HBM)."""
+        rc = lib.vgpa_initialization(self._h, float(t0), x_ptr, self.n_x if x_stride is None else x_stride,
+                                     stream or None)
+        raise_for(rc, self._h)
+
     def eval_full(self, x, problem=0):
         """Everything the reference caches or passes between stages, for one problem."""
         x = f64(x).reshape(-1)

@@ -89,6 +89,12 @@ class VarGP(object):
             b0[-1] = a0[-1].diagonal() * mt0[-1]
         return np.concatenate((a0.ravel(), b0.ravel()))
 
+    def initialization_gpu(self):
+        """The same x0 computed by the CUDA library (vgpa_initialization_host): the single-problem
+        view of the batched on-device initialisation that ensembles use (BatchEvaluator.initialization /
+        .initialization_device); agrees with initialization() to rounding (tests/test_gpu_init.py)."""
+        return self._ev.initialization(float(self.model.time_window[0]))[0]
+
     # -- the hot path -------------------------------------------------------------------
     def _evaluate(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
