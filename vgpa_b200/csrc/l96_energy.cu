@@ -98,6 +98,9 @@ __device__ __forceinline__ void bar_sync()
 template <int ID>
 __device__ __forceinline__ void bar_arrive()
 {
+    // producer side of the PTX producer/consumer pattern (st.shared; bar.arrive | bar.sync; ld.shared);
+    // the block-scope fence makes the ordering of the preceding shared-memory stores explicit
+    __threadfence_block();
     asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(128) : "memory");
 }
 
