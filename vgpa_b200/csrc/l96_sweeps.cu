@@ -538,6 +538,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 parA[nxt] ^= 1u;
                 next_ready = true;
             }
+            if (sidx == 1 && stage_kind(METHOD, 1) == K_MID) __syncthreads();   // A_mid complete in slot cur
             const double* vX = (sidx == 0) ? sm.lam : sm.lt[(sidx - 1) & 1];
             double* Tw = sm.Tb[tsel];
             tsel ^= 1;
@@ -550,7 +551,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             } else {
                 if (kind == K_CUR)       mma_rowx<0, 0, K_CUR>(Hc, edf0, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
                 else if (kind == K_NEXT) mma_rowx<0, 0, K_NEXT>(Hc, edf0, nullptr, An, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
-                else                     mma_rowx<0, 1, K_MID>(Hc, edf0, nullptr, Ac, An, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);
+                else                     mma_rowx<0, 0, K_CUR>(Hc, edf0, nullptr, Ac, nullptr, Ac, An, vX, 0.0, irow, g, q, lane, acc, yv);  // slot cur holds A_mid
             }
             row_to_smem(Tw, irow, q, acc);
             {
@@ -561,6 +562,27 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 if (sidx < NS - 1 && q == 0) sm.lt[sidx & 1][irow] = sm.lam[irow] - (next_coef(METHOD, sidx) * dt) * ks;
             }
             __syncthreads();  // the only barrier of the stage: transpose buffer and next lambda operand complete
+            if (sidx == 0 && NS > 1 && stage_kind(METHOD, 1) == K_MID) {
+                // Every warp has finished its last product with A_t (gradient and stage 0): turn slot
+                // cur into the midpoint A_mid = (A_t + A_{t-1}) / 2 IN PLACE, each warp its own eight
+                // rows, so that the midpoint stages read one buffer (half the B-fragment traffic of
+                // those stages and no per-fragment averaging).  The slot is refilled with A_{t-2}
+                // after the last stage, as before.
+                if (!next_ready) {
+                    mbar_wait(&sm.barA[nxt], parA[nxt]);
+                    parA[nxt] ^= 1u;
+                    next_ready = true;
+                }
+                double* Aw = sm.Ab[cur];
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                    const int c = lane + 32 * n, r = c / 20, ch = c - 20 * r;
+                    const int o = sm_idx(8 * w + r, 2 * ch);
+                    const double2 a2 = *reinterpret_cast<const double2*>(&Aw[o]);
+                    const double2 b2 = *reinterpret_cast<const double2*>(&An[o]);
+                    *reinterpret_cast<double2*>(&Aw[o]) = make_double2(0.5 * (a2.x + b2.x), 0.5 * (a2.y + b2.y));
+                }
+            }
             if (sidx == 0 && with_grad) {
                 // S_t, m_t, b_t are dead (gradient written by every warp): fetch index t-1
                 if (tid == 0) {
