@@ -42,6 +42,8 @@ class VarGP(object):
         self._device = device
         self._ev_obj = None
         self._x_cached = None
+        self._x_obj = None
+        self._x_probe = None
         self._f_cached = None
         self._g_cached = None
         self._full_for = None
@@ -97,17 +99,36 @@ class VarGP(object):
 
     # -- the hot path -------------------------------------------------------------------
     def _evaluate(self, x):
+        xin = x
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
         F, G = self._ev.eval(x, want_grad=True)
         self.n_eval += 1
         self._x_cached = x.copy()
+        self._x_obj = xin                       # the caller's array object (identity shortcut below)
+        self._x_probe = x[::self._probe_step(x.size)].copy()
         self._f_cached = float(F[0])
         self._g_cached = G[0]
         self._full_for = None
 
+    @staticmethod
+    def _probe_step(n):
+        return max(1, n // 2048)
+
     def _is_cached(self, x):
-        return self._x_cached is not None and x.size == self._x_cached.size and \
-            np.array_equal(np.asarray(x).reshape(-1), self._x_cached)
+        """Was the last evaluation at this x?  (The reference does not check at all: its gradient(x)
+        trusts the caller, variational.py:214-226.)  A strided probe of ~2000 entries rejects a new
+        point without touching the 13 MB array; the SCG's df(x) right after f(x) passes the same
+        array object, which is accepted on the probe alone; anything else gets the full comparison."""
+        if self._x_cached is None:
+            return False
+        xa = np.asarray(x).reshape(-1)
+        if xa.size != self._x_cached.size:
+            return False
+        if not np.array_equal(xa[::self._probe_step(xa.size)], self._x_probe):
+            return False
+        if x is self._x_obj:
+            return True
+        return np.array_equal(xa, self._x_cached)
 
     def free_energy(self, x):
         """E0 + Esde + Eobs as a Python float (variational.py:141-200)."""
