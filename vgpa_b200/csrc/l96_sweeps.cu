@@ -13,8 +13,9 @@
 // CTA = 160 threads = 5 warps; warp w owns rows 8w..8w+7 of every matrix AND vector:
 //   * its 8 x 40 tile-row of each 40 x 40 product runs on the FP64 tensor cores
 //     (mma.sync m8n8k4 f64, SASS DMMA): per k-step one A fragment and five B fragments
-//     from shared memory (pitch 44 doubles: conflict-free for both fragment shapes)
-//     feed five DMMAs; accumulators stay in registers;
+//     from shared memory (skewed layout of common.cuh, sm_idx: conflict-free for the fragment
+//     loads, the 16-byte accumulator accesses and the transposed reads) feed five DMMAs;
+//     accumulators stay in registers;
 //   * the mean / lambda recurrences (40 x 40 mat-vecs) ride in the same k-loop: the A
 //     fragment already in registers times the vector entry, reduced over the four
 //     lanes of a fragment row with two shuffles;
@@ -78,57 +79,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
-}
-
-// ---- tile-row product with a fused mat-vec -------------------------------------
-//   acc[J] = sum_k L(irow, k) * R(k, 8J + ...)          (five DMMAs per k-step)
-//   yv     = sum_k Av(irow, k) * v[k]                     (one DFMA per k-step)
-// Operand kinds: 0 = plain buffer, 1 = midpoint 0.5*(buf0 + buf1);
-// LK = 2: fused left operand isg*L0 - 2*L1 (gradient assembly; then Av = L0).
-// VK: which matrix feeds the mat-vec: -1 none, 3 = the (possibly fused) left operand's
-// first buffer kind LK, else the kind of (V0, V1) loaded separately.
-template <int LK, int RK, int VK>
-__device__ __forceinline__ void mma_row(const double* __restrict__ L0, const double* __restrict__ L1,
-                                        const double* __restrict__ R0, const double* __restrict__ R1,
-                                        const double* __restrict__ V0, const double* __restrict__ V1,
-                                        const double* __restrict__ v, double isg_row, int irow, int g, int q,
-                                        double (&acc)[5][2], double& yv)
-{
-#pragma unroll
-    for (int J = 0; J < 5; ++J) acc[J][0] = acc[J][1] = 0.0;
-    double y = 0.0;
-    const int la = sm_idx(irow, q);   // A fragment: row irow, col k0+q
-    const int lb = sm_boff(q, g);     // B fragment: row k0+q, col 8J+g
-#pragma unroll
-    for (int k0 = 0; k0 < D; k0 += 4) {
-        double a, av = 0.0;
-        if (LK == 0) a = L0[la + k0];
-        else if (LK == 1) a = 0.5 * (L0[la + k0] + L1[la + k0]);
-        else {
-            av = L0[la + k0];
-            a = fma(isg_row, av, -2.0 * L1[la + k0]);
-        }
-        if (VK == 3) {
-            if (LK != 2) av = a;
-        } else if (VK == K_CUR) av = V0[la + k0];
-        else if (VK == K_NEXT) av = V1[la + k0];
-        else if (VK == K_MID) av = 0.5 * (V0[la + k0] + V1[la + k0]);
-        if (VK >= 0) y = fma(av, v[k0 + q], y);
-        double b[5];
-#pragma unroll
-        for (int J = 0; J < 5; ++J) {
-            const int o = lb + (k0 >> 3) * SM_R8 + ((k0 >> 2) & 1) * SM_BH + 8 * J;
-            if (RK == 0) b[J] = R0[o];
-            else b[J] = 0.5 * (R0[o] + R1[o]);
-        }
-#pragma unroll
-        for (int J = 0; J < 5; ++J) dmma(acc[J][0], acc[J][1], a, b[J]);
-    }
-    if (VK >= 0) {
-        y += __shfl_xor_sync(0xffffffffu, y, 1);
-        y += __shfl_xor_sync(0xffffffffu, y, 2);
-    }
-    yv = y;
 }
 
 // accumulator tile-row -> shared memory (each lane: two adjacent doubles per tile)
