@@ -302,6 +302,10 @@ def run_b200(args):
         except OSError:
             pass
         Be = 1024 if avail_gb >= 64.0 * world else 512
+        if world > 1:   # every rank must use the same step size: take the smallest choice
+            tb = torch.tensor([Be], dtype=torch.int64, device=dev)
+            dist.all_reduce(tb, op=dist.ReduceOp.MIN)
+            Be = int(tb.item())
     Be = min(Be, B)
     xe = PinnedArray((Be, N_X))
     ge = PinnedArray((Be, N_X))
