@@ -109,9 +109,40 @@ class Simulation(object):
         vgpa.close()
 
     def save(self):
-        out = Path(self.name + ".npz")
-        np.savez_compressed(out, **{k: np.asarray(v) for k, v in self.output.items()})
+        """simulation.py:269-311: every entry of `output` as one gzip-compressed dataset of
+        `<name>.h5` (scalars as 1-D arrays).  Without h5py (it is not a dependency of the CUDA
+        path) the same keys go to `<name>.npz`; `load` reads either."""
+        if not self.output:
+            print(f" {self.__class__.__name__}: Simulation data structure 'output' is empty.")
+            return
+        stem = self.name.strip().replace(" ", "_")
+        data = {k: np.atleast_1d(v) if np.isscalar(v) else np.asarray(v) for k, v in self.output.items()}
+        try:
+            import h5py
+        except ImportError:
+            h5py = None
+        if h5py is not None:
+            out = Path(stem + ".h5")
+            with h5py.File(out, "w") as out_file:
+                for key, val in data.items():
+                    out_file.create_dataset(key, data=val, shape=val.shape, compression="gzip")
+        else:
+            out = Path(stem + ".npz")
+            np.savez_compressed(out, **data)
         print(f" Saved the results to: {out}")
+
+
+def load(filename=None):
+    """simulation.py:316-345: the dictionary written by Simulation.save (.h5 or .npz)."""
+    if filename is None:
+        raise RuntimeError(" load_data: No input file is given.")
+    path = Path(filename)
+    if path.suffix == ".npz":
+        with np.load(path, allow_pickle=False) as z:
+            return {k: z[k] for k in z.files}
+    import h5py
+    with h5py.File(path, "r") as input_file:
+        return {key: np.array(input_file[key]) for key in input_file}
 
 
 def main(params_file=None, data_file=None):
