@@ -42,6 +42,9 @@ constexpr int ROWB = D * 8;    // bytes of one matrix row in HBM
 constexpr int NMMA = 5;        // MMA warps = tile rows
 constexpr int NTH = 32 * NMMA;
 
+constexpr int SMALL_LAUNCH = 148;   // launches of at most one CTA per SM prefetch their streams into L2
+constexpr int PF_STEPS = 4;         // ... this many time indices ahead
+
 enum { K_CUR = 0, K_MID = 1, K_NEXT = 2 };
 
 __host__ __device__ constexpr int n_stages(int m) { return m == ODE_EULER ? 1 : (m == ODE_RK4 ? 4 : 2); }
@@ -368,6 +371,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     const bool keep = a.lam_out != nullptr && lp == 0;
     const double* oy = dense ? nullptr : b.obs_y + p * b.obs_y_stride;
     const double dt = b.dt, dtm = b.dt_model;
+    const bool small_launch = gridDim.x <= SMALL_LAUNCH;
     const double theta = (b.theta != nullptr) ? b.theta[p * b.theta_stride] : 0.0;
 
     if (tid == 0) {
@@ -429,6 +433,16 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
                 *reinterpret_cast<double2*>(&a.psi_out[(long long)t * D * D + irow * D + 8 * J + 2 * q]) =
                     make_double2(Pc[J][0], Pc[J][1]);
             if (q == 0) a.lam_out[(long long)t * D + irow] = sm.lam[irow];
+        }
+        // Small launches only (at most one CTA per SM: nothing else hides HBM latency, which is what a
+        // single problem then waits for): this warp's eight rows of the three streams, PF_STEPS
+        // indices ahead, into L2.  With full waves the same prefetch was measured harmful (evictions);
+        // in the forward sweep it does not pay even for one problem.
+        if (small_launch && lane == 0 && t >= PF_STEPS) {
+            const long long o = (long long)(t - PF_STEPS) * D * D + (long long)(8 * w) * D;
+            bulk_prefetch_l2(A + o, 8 * ROWB);
+            bulk_prefetch_l2(dEs + o, 8 * ROWB);
+            if (with_grad) bulk_prefetch_l2(st + o, 8 * ROWB);
         }
         // register prefetch of dE/dS[t-1], dE/dm[t-1] (consumed one or two stages later)
         if (t >= 1) {
