@@ -313,14 +313,21 @@ __device__ __forceinline__ void mma_rowx(const double (&Xc)[5][2], const double 
     const int lb = sm_boff(q, g);
     const int srcb = (lane & ~3) + (q >> 1);
     const bool odd = (q & 1) != 0;
+    // the left-operand entry of k-step n+1 is fetched (two shuffles) before the DMMAs of k-step n are
+    // issued, so that the shuffle latency hides behind the tensor work
+    auto fetch = [&](int n) {
+        const int src = srcb + ((n & 1) << 1);
+        const double x0 = __shfl_sync(0xffffffffu, Xc[n >> 1][0], src);
+        const double x1 = __shfl_sync(0xffffffffu, Xc[n >> 1][1], src);
+        return odd ? x1 : x0;
+    };
+    double xnext = fetch(0);
 #pragma unroll
     for (int n = 0; n < D / 4; ++n) {
         const int k0 = 4 * n;
         // entry (irow, k0 + q) sits in tile n/2 at lane 2*(n&1) + q/2 of this row group, slot q&1
-        const int src = srcb + ((n & 1) << 1);
-        const double x0 = __shfl_sync(0xffffffffu, Xc[n >> 1][0], src);
-        const double x1 = __shfl_sync(0xffffffffu, Xc[n >> 1][1], src);
-        const double xv = odd ? x1 : x0;
+        const double xv = xnext;
+        if (n + 1 < D / 4) xnext = fetch(n + 1);
         double a, av = 0.0;
         if (MODE == 2) {
             av = A0[la + k0];
