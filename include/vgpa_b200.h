@@ -177,6 +177,39 @@ int vgpa_obs_energy(int device, int D, int N, int M, const int64_t *obs_t, const
 int vgpa_initialization(vgpa_handle *h, double t0, double *d_x, int64_t x_stride, void *stream);
 int vgpa_initialization_host(vgpa_handle *h, double t0, double *x, int64_t x_stride);
 
+/* Batched sample paths for ensembles: the Euler-Maruyama loops of DoubleWell / OrnsteinUhlenbeck /
+ * Lorenz63 / Lorenz96 .make_trajectory (double_well.py:122-166, ornstein_uhlenbeck.py:128-161,
+ * lorenz_63.py:181-233, lorenz_96.py:249-314) for B paths at once.  The standard-normal draws are an
+ * INPUT in the layout the reference draws them -- z: (D, N) per path, row 0 of the time axis unused --
+ * so a host generator seeded like the reference gives the reference's path bit for bit (every
+ * operation is one correctly rounded IEEE operation in the reference's order, no FMA contraction).
+ *   theta : DW [theta], OU [theta, mu], L63 [sigma, rho, beta], L96 [F]      (per path, stride 0 = shared)
+ *   sigma : (D) diagonal of the system noise;  x_init: (D) state at t0 -- required for DW / OU
+ *           (their start consumes the generator, double_well.py:145-151), NULL for L63 / L96 = the
+ *           reference's 5000-step burn-in from its fixed starting point
+ *   path  : (N, D) per path, row stride path_stride
+ * vgpa_make_trajectory: HOST buffers, synchronous.  _device: DEVICE buffers, asynchronous on `stream`. */
+int vgpa_make_trajectory(int device, int model, int N, int B, double dt, const double *theta,
+                         int64_t theta_stride, const double *sigma, int64_t sigma_stride,
+                         const double *x_init, int64_t x_init_stride, const double *z, int64_t z_stride,
+                         double *path, int64_t path_stride);
+int vgpa_make_trajectory_device(int device, int model, int N, int B, double dt, const double *d_theta,
+                                int64_t theta_stride, const double *d_sigma, int64_t sigma_stride,
+                                const double *d_x_init, int64_t x_init_stride, const double *d_z,
+                                int64_t z_stride, double *d_path, int64_t path_stride, void *stream);
+
+/* StochasticProcess.collect_obs (stochastic_process.py:130-230) for B observation sets:
+ * obs_y[p][j][i] = path[p][obs_t[j]][i] + sqrt(R[p][i]) * xi[p][i][j]   (xi: (D, M) draws, the
+ * reference's layout; R: (D) diagonal; obs_y: (M, D)).  The observation indices themselves
+ * (np.linspace, :172-175) are host-side integers and stay with the caller. */
+int vgpa_collect_obs(int device, int D, int N, int M, int B, const int64_t *obs_t, const double *R,
+                     int64_t R_stride, const double *path, int64_t path_stride, const double *xi,
+                     int64_t xi_stride, double *obs_y, int64_t obs_y_stride);
+int vgpa_collect_obs_device(int device, int D, int N, int M, int B, const int64_t *d_obs_t,
+                            const double *d_R, int64_t R_stride, const double *d_path,
+                            int64_t path_stride, const double *d_xi, int64_t xi_stride,
+                            double *d_obs_y, int64_t obs_y_stride, void *stream);
+
 /* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
 void *vgpa_host_alloc(int64_t bytes);
 void vgpa_host_free(void *p);

@@ -147,6 +147,10 @@ class Oracle:
         L.oracle_eval_batch.argtypes = [C.POINTER(_CProblem), C.c_int, _dp, C.c_longlong, _dp, _dp,
                                         C.c_longlong, C.c_int]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_make_trajectory.restype = C.c_int
+        L.oracle_make_trajectory.argtypes = [C.c_int, C.c_int, C.c_double] + [_dp] * 5
+        L.oracle_collect_obs.restype = None
+        L.oracle_collect_obs.argtypes = [C.c_int, C.c_int, _lp, _dp, _dp, _dp, _dp]
 
     @staticmethod
     def _raise(rc):
@@ -221,6 +225,29 @@ class Oracle:
                                         X.shape[1], threads)
         self._raise(rc)
         return F, G
+
+    def make_trajectory(self, model, N, dt, theta, sigma_diag, z, x_init=None):
+        """<Model>.make_trajectory given its standard-normal draws z ((D, N); (N,) for D = 1)."""
+        key = model.upper()
+        D = {"DW": 1, "OU": 1, "L63": 3, "L96": 40}[key]
+        a = [np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64) for v in (theta, sigma_diag, z)]
+        xi = None if x_init is None else np.ascontiguousarray(np.atleast_1d(x_init), dtype=np.float64)
+        assert a[2].size == N * D and a[1].size == D
+        path = np.empty(N * D)
+        self._raise(self.lib.oracle_make_trajectory(MODELS[key], int(N), float(dt), _p(a[0]), _p(a[1]), _p(xi),
+                                                    _p(a[2]), _p(path)))
+        return path if D == 1 else path.reshape(N, D)
+
+    def collect_obs(self, path, obs_t, R_diag, xi):
+        """StochasticProcess.collect_obs given its draws xi ((D, M); (M,) for D = 1)."""
+        R = np.ascontiguousarray(np.atleast_1d(R_diag), dtype=np.float64)
+        D = R.size
+        ot = np.ascontiguousarray(np.asarray(obs_t, dtype=np.int64).ravel())
+        path, xi = (np.ascontiguousarray(v, dtype=np.float64) for v in (path, xi))
+        assert xi.size == D * ot.size and path.size % D == 0
+        out = np.empty(ot.size * D)
+        self.lib.oracle_collect_obs(D, ot.size, ot.ctypes.data_as(_lp), _p(R), _p(path), _p(xi), _p(out))
+        return out if D == 1 else out.reshape(ot.size, D)
 
     def num_threads(self):
         return int(self.lib.oracle_num_threads())

@@ -1129,3 +1129,75 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Data generation.  The standard-normal draws are inputs, in the layout the
+ * reference draws them; built with -ffp-contract=off, so every line below is the reference's
+ * sequence of IEEE operations.
+ *   DoubleWell.make_trajectory         src/dynamics/double_well.py:122-166
+ *   OrnsteinUhlenbeck.make_trajectory  src/dynamics/ornstein_uhlenbeck.py:128-161
+ *   Lorenz63.make_trajectory / l63     src/dynamics/lorenz_63.py:181-233, :8-37
+ *   Lorenz96.make_trajectory / l96     src/dynamics/lorenz_96.py:249-314, :85-101
+ * theta: DW [theta], OU [theta, mu], L63 [sigma, rho, beta], L96 [F].  sigma: (D) diagonal.
+ * x_init: (D) state at t0 (DW / OU: required; L63 / L96: NULL = 5000 burn-in steps of 1e-3).
+ * z: (D, N) draws; path: (N, D).
+ * ------------------------------------------------------------------------------------------ */
+static void gen_l63(const double *x, const double *u, double *f)
+{
+    f[0] = u[0] * (x[1] - x[0]);
+    f[1] = (u[1] - x[2]) * x[0] - x[1];
+    f[2] = x[0] * x[1] - u[2] * x[2];
+}
+
+static void gen_l96(const double *x, double u, int D, double *f)
+{
+    for (int i = 0; i < D; ++i)                       /* (roll(x,-1) - roll(x,+2)) * roll(x,+1) - x + u */
+        f[i] = (x[(i + 1) % D] - x[(i + D - 2) % D]) * x[(i + D - 1) % D] - x[i] + u;
+}
+
+int oracle_make_trajectory(int model, int N, double dt, const double *theta, const double *sigma,
+                           const double *x_init, const double *z, double *path)
+{
+    if (model == MODEL_DW || model == MODEL_OU) {
+        if (!x_init) return 1;
+        const double sq = sqrt(sigma[0] * dt);
+        double x = x_init[0];
+        path[0] = x;
+        for (int t = 1; t < N; ++t) {
+            const double ek = sq * z[t];
+            if (model == MODEL_DW) x = x + 4.0 * x * (theta[0] - x * x) * dt + ek;     /* double_well.py:158-159 */
+            else x = x + theta[0] * (theta[1] - x) * dt + ek;                           /* ornstein_uhlenbeck.py:155 */
+            path[t] = x;
+        }
+        return 0;
+    }
+    const int D = (model == MODEL_L63) ? 3 : 40;
+    double x[40], f[40], sq[40];
+    for (int i = 0; i < D; ++i) sq[i] = sqrt(sigma[i] * dt);    /* cholesky of a diagonal matrix */
+    if (x_init) {
+        memcpy(x, x_init, sizeof(double) * D);
+    } else {
+        for (int i = 0; i < D; ++i) x[i] = (model == MODEL_L63) ? 1.0 : theta[0];
+        if (model == MODEL_L96) x[D / 2] += 1.0e-3;
+        for (int k = 0; k < 5000; ++k) {
+            if (model == MODEL_L63) gen_l63(x, theta, f); else gen_l96(x, theta[0], D, f);
+            for (int i = 0; i < D; ++i) x[i] = x[i] + f[i] * 1.0e-3;
+        }
+    }
+    memcpy(path, x, sizeof(double) * D);
+    for (int t = 1; t < N; ++t) {
+        if (model == MODEL_L63) gen_l63(x, theta, f); else gen_l96(x, theta[0], D, f);
+        for (int i = 0; i < D; ++i) x[i] = x[i] + f[i] * dt + sq[i] * z[(size_t)i * N + t];
+        memcpy(path + (size_t)t * D, x, sizeof(double) * D);
+    }
+    return 0;
+}
+
+/* StochasticProcess.collect_obs (stochastic_process.py:177-226): xi is (D, M), obs_y is (M, D). */
+void oracle_collect_obs(int D, int M, const long long *obs_t, const double *R, const double *path,
+                        const double *xi, double *obs_y)
+{
+    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < D; ++i)
+            obs_y[(size_t)j * D + i] = path[(size_t)obs_t[j] * D + i] + sqrt(R[i]) * xi[(size_t)i * M + j];
+}

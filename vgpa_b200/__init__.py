@@ -12,6 +12,7 @@ import importlib
 _EXPORTS = {
     "BatchEvaluator": "engine", "model_energy": "engine", "obs_energy": "engine",
     "solve_bwd": "engine", "solve_fwd": "engine",
+    "make_trajectories": "engine", "collect_observations": "engine",
     "StochasticProcess": "dynamics", "DoubleWell": "dynamics", "OrnsteinUhlenbeck": "dynamics",
     "Lorenz63": "dynamics", "Lorenz96": "dynamics", "dynamical_systems": "dynamics",
     "FwdOde": "ode", "BwdOde": "ode", "GaussianLikelihood": "likelihood", "PriorKL0": "prior",

@@ -76,6 +76,14 @@ def _load():
     lib.vgpa_model_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 13
     lib.vgpa_obs_energy.restype = C.c_int
     lib.vgpa_obs_energy.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _ip] + [_dp] * 8
+    i64 = C.c_int64
+    traj = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_void_p, i64] * 5
+    obs = [C.c_int] * 5 + [C.c_void_p] + [C.c_void_p, i64] * 4
+    for name, args in (("vgpa_make_trajectory", traj), ("vgpa_make_trajectory_device", traj + [C.c_void_p]),
+                       ("vgpa_collect_obs", obs), ("vgpa_collect_obs_device", obs + [C.c_void_p])):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
     lib.vgpa_host_alloc.restype = C.c_void_p
     lib.vgpa_host_alloc.argtypes = [C.c_int64]
     lib.vgpa_host_free.restype = None

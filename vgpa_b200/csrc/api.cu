@@ -875,6 +875,146 @@ int vgpa_initialization_host(vgpa_handle* h, double t0, double* x, int64_t x_str
     return VGPA_OK;
 }
 
+// ---- batched sample paths and observations (datagen.cu) -------------------------
+static int model_dim(int model) { return model == VGPA_MODEL_L96 ? 40 : (model == VGPA_MODEL_L63 ? 3 : 1); }
+static int traj_ntheta(int model) { return model == VGPA_MODEL_L63 ? 3 : (model == VGPA_MODEL_OU ? 2 : 1); }
+
+static int check_traj_args(int model, int N, int B, double dt, const void* theta, const void* sigma,
+                           const void* x_init, const void* z, const void* path, int64_t z_stride, int64_t path_stride)
+{
+    if (model < 0 || model > 3) { g_create_error = "Unknown stochastic model"; return VGPA_EINVAL; }
+    const int D = model_dim(model);
+    if (N < 1 || B < 1) { g_create_error = "need N >= 1 time points and B >= 1 paths"; return VGPA_EINVAL; }
+    if (!(dt > 0.0)) { g_create_error = "Discrete time step should be strictly positive"; return VGPA_EINVAL; }
+    if (!theta || !sigma || !z || !path) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    if (D == 1 && !x_init) { g_create_error = "x_init is required for the 1-D models"; return VGPA_EINVAL; }
+    if ((z_stride != 0 && z_stride < (int64_t)N * D) || (B > 1 && path_stride < (int64_t)N * D)) {
+        g_create_error = "z_stride / path_stride shorter than one path"; return VGPA_EINVAL;
+    }
+    return VGPA_OK;
+}
+
+int vgpa_make_trajectory_device(int device, int model, int N, int B, double dt, const double* d_theta, int64_t theta_stride,
+                                const double* d_sigma, int64_t sigma_stride, const double* d_x_init, int64_t x_init_stride,
+                                const double* d_z, int64_t z_stride, double* d_path, int64_t path_stride, void* stream)
+{
+    if (int rc = check_traj_args(model, N, B, dt, d_theta, d_sigma, d_x_init, d_z, d_path, z_stride, path_stride)) return rc;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    TrajArgs a{model, model_dim(model), N, B, dt, d_theta, theta_stride, d_sigma, sigma_stride, d_x_init, x_init_stride,
+               d_z, z_stride, d_path, path_stride};
+    launch_trajectories(a, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_create_error = std::string("CUDA error in vgpa_make_trajectory_device: ") + cudaGetErrorString(e); return VGPA_ECUDA; }
+    return VGPA_OK;
+}
+
+// copy `rows` rows of `len` elements, `stride` apart (0 = one shared row), to a compact device buffer
+static cudaError_t stage_rows(DevBuf& dst, const double* src, int64_t stride, int64_t len, int rows, long long* dstride)
+{
+    const int r = stride == 0 ? 1 : rows;
+    cudaError_t e = dst.alloc(sizeof(double) * (size_t)len * r);
+    if (e != cudaSuccess) return e;
+    *dstride = stride == 0 ? 0 : len;
+    if (r == 1 || stride == len) return cudaMemcpy(dst.p, src, sizeof(double) * (size_t)len * r, cudaMemcpyHostToDevice);
+    return cudaMemcpy2D(dst.p, sizeof(double) * len, src, sizeof(double) * stride, sizeof(double) * len, r, cudaMemcpyHostToDevice);
+}
+
+int vgpa_make_trajectory(int device, int model, int N, int B, double dt, const double* theta, int64_t theta_stride,
+                         const double* sigma, int64_t sigma_stride, const double* x_init, int64_t x_init_stride,
+                         const double* z, int64_t z_stride, double* path, int64_t path_stride)
+{
+    if (int rc = check_traj_args(model, N, B, dt, theta, sigma, x_init, z, path, z_stride, path_stride)) return rc;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const int D = model_dim(model);
+    const int64_t len = (int64_t)N * D;
+    DevBuf dth, dsg, dxi, dz, dp;
+    auto cleanup = [&]() { for (DevBuf* q : {&dth, &dsg, &dxi, &dz, &dp}) q->release(); };
+    TrajArgs a{};
+    a.model = model; a.D = D; a.N = N; a.B = B; a.dt = dt;
+    cudaError_t e;
+    if ((e = stage_rows(dth, theta, theta_stride, traj_ntheta(model), B, &a.theta_stride)) != cudaSuccess ||
+        (e = stage_rows(dsg, sigma, sigma_stride, D, B, &a.sigma_stride)) != cudaSuccess ||
+        (x_init && (e = stage_rows(dxi, x_init, x_init_stride, D, B, &a.x_init_stride)) != cudaSuccess) ||
+        (e = stage_rows(dz, z, z_stride, len, B, &a.z_stride)) != cudaSuccess ||
+        (e = dp.alloc(sizeof(double) * (size_t)len * B)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_make_trajectory: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    a.theta = dth.as<double>(); a.sigma = dsg.as<double>(); a.x_init = x_init ? dxi.as<double>() : nullptr;
+    a.z = dz.as<double>(); a.path = dp.as<double>(); a.path_stride = len;
+    launch_trajectories(a, nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+        e = cudaMemcpy2D(path, sizeof(double) * (B > 1 ? path_stride : len), dp.p, sizeof(double) * len, sizeof(double) * len, B,
+                         cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) { g_create_error = std::string("CUDA error in vgpa_make_trajectory: ") + cudaGetErrorString(e); return VGPA_ECUDA; }
+    return VGPA_OK;
+}
+
+static int check_obs_args(int D, int N, int M, int B, const int64_t* obs_t /* host, or NULL = not checked */)
+{
+    if (D != 1 && D != 3 && D != 40) { g_create_error = "unsupported state dimension (1, 3 or 40)"; return VGPA_EINVAL; }
+    if (N < 1 || M < 0 || B < 1) { g_create_error = "need N >= 1, M >= 0, B >= 1"; return VGPA_EINVAL; }
+    for (int j = 0; obs_t && j < M; ++j)
+        if (obs_t[j] < 0 || obs_t[j] >= N) { g_create_error = "observation index outside the time grid"; return VGPA_EINVAL; }
+    return VGPA_OK;
+}
+
+int vgpa_collect_obs_device(int device, int D, int N, int M, int B, const int64_t* d_obs_t, const double* d_R, int64_t R_stride,
+                            const double* d_path, int64_t path_stride, const double* d_xi, int64_t xi_stride,
+                            double* d_obs_y, int64_t obs_y_stride, void* stream)
+{
+    if (int rc = check_obs_args(D, N, M, B, nullptr)) return rc;
+    if (!d_obs_t || !d_R || !d_path || !d_xi || !d_obs_y) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    ObsArgs a{D, N, M, B, reinterpret_cast<const long long*>(d_obs_t), d_R, R_stride, d_path, path_stride, d_xi, xi_stride,
+              d_obs_y, obs_y_stride};
+    launch_collect_obs(a, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_create_error = std::string("CUDA error in vgpa_collect_obs_device: ") + cudaGetErrorString(e); return VGPA_ECUDA; }
+    return VGPA_OK;
+}
+
+int vgpa_collect_obs(int device, int D, int N, int M, int B, const int64_t* obs_t, const double* R, int64_t R_stride,
+                     const double* path, int64_t path_stride, const double* xi, int64_t xi_stride, double* obs_y,
+                     int64_t obs_y_stride)
+{
+    if (!obs_t || !R || !path || !xi || !obs_y) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
+    if (int rc = check_obs_args(D, N, M, B, obs_t)) return rc;
+    if (M == 0) return VGPA_OK;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
+    const int64_t plen = (int64_t)N * D, olen = (int64_t)M * D;
+    DevBuf dt_, dR, dp, dx, dy;
+    auto cleanup = [&]() { for (DevBuf* q : {&dt_, &dR, &dp, &dx, &dy}) q->release(); };
+    ObsArgs a{};
+    a.D = D; a.N = N; a.M = M; a.B = B;
+    cudaError_t e;
+    if ((e = dt_.alloc(sizeof(int64_t) * M)) != cudaSuccess ||
+        (e = cudaMemcpy(dt_.p, obs_t, sizeof(int64_t) * M, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = stage_rows(dR, R, R_stride, D, B, &a.R_stride)) != cudaSuccess ||
+        (e = stage_rows(dp, path, path_stride, plen, B, &a.path_stride)) != cudaSuccess ||
+        (e = stage_rows(dx, xi, xi_stride, olen, B, &a.xi_stride)) != cudaSuccess ||
+        (e = dy.alloc(sizeof(double) * (size_t)olen * B)) != cudaSuccess) {
+        cleanup();
+        g_create_error = std::string("CUDA error in vgpa_collect_obs: ") + cudaGetErrorString(e);
+        return VGPA_ECUDA;
+    }
+    a.obs_t = dt_.as<long long>(); a.R = dR.as<double>(); a.path = dp.as<double>(); a.xi = dx.as<double>();
+    a.obs_y = dy.as<double>(); a.obs_y_stride = olen;
+    launch_collect_obs(a, nullptr);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+        e = cudaMemcpy2D(obs_y, sizeof(double) * (B > 1 ? obs_y_stride : olen), dy.p, sizeof(double) * olen, sizeof(double) * olen,
+                         B, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) { g_create_error = std::string("CUDA error in vgpa_collect_obs: ") + cudaGetErrorString(e); return VGPA_ECUDA; }
+    return VGPA_OK;
+}
+
 void* vgpa_host_alloc(int64_t bytes)
 {
     void* p = nullptr;

@@ -44,6 +44,25 @@ struct Extra {
     double* parts; // (3) E0, Esde, Eobs
 };
 
+// Batched sample paths / observations (datagen.cu); device pointers, strides in elements (0 = shared).
+struct TrajArgs {
+    int model, D, N, B;
+    double dt;
+    const double* theta;  long long theta_stride;    // DW [theta], OU [theta, mu], L63 [sigma, rho, beta], L96 [F]
+    const double* sigma;  long long sigma_stride;    // (D) diagonal of the system noise
+    const double* x_init; long long x_init_stride;   // (D) state at t0; null (L63, L96) = the reference's burn-in
+    const double* z;      long long z_stride;        // (D, N) standard-normal draws, the reference's layout
+    double* path;         long long path_stride;     // (N, D)
+};
+struct ObsArgs {
+    int D, N, M, B;
+    const long long* obs_t;                          // (M)
+    const double* R;      long long R_stride;        // (D) diagonal of the observation noise
+    const double* path;   long long path_stride;     // (N, D)
+    const double* xi;     long long xi_stride;       // (D, M) standard-normal draws
+    double* obs_y;        long long obs_y_stride;    // (M, D)
+};
+
 // ---- shared-memory layout of a 40 x 40 matrix in the D = 40 kernels -----------------------
 // Rows are contiguous (one bulk / cp.async copy per row); row PAIRS are 84 doubles apart:
 //   address(row, col) = 84 * (row >> 1) + 40 * (row & 1) + col      (1680 doubles per matrix)
@@ -101,6 +120,10 @@ void launch_hyper(int model, int D, int N, double dt_model, const double* theta,
 // dEobs_dr of the 1-D likelihood (N values, zero except at obs_t).
 void launch_obs_dr(int N, int M, const long long* obs_t, const double* obs_y, const double* R,
                    const double* mt, const double* st, double* dr, cudaStream_t stream);
+
+// Euler-Maruyama sample paths and noisy observations for ensembles (make_trajectory / collect_obs).
+void launch_trajectories(const TrajArgs& a, cudaStream_t st);
+void launch_collect_obs(const ObsArgs& a, cudaStream_t st);
 
 // Dense jump tables dEobs_dm (N,D), dEobs_ds (N,D,D) (GaussianLikelihood.gradients).
 void launch_jump_tables(int D, int N, int M, const long long* obs_t, const double* obs_y, const double* R,

@@ -7,9 +7,13 @@ same properties (`sigma`, `theta`, `inverse_sigma`, `single_dim`, `sample_path`,
 random streams, and `energy(A, b, m, S, obs_t)` with the reference's return
 structure -- but `energy` runs on the GPU (vgpa_model_energy), never on the CPU.
 
-The data-generation methods are plain numpy (they are not on the hot path); they
-consume the numpy Generator exactly as the reference does so that the same seed
-gives the same trajectory, observations and initial moments.
+The data-generation methods consume the numpy Generator exactly as the reference
+does, so that the same seed gives the same trajectory, observations and initial
+moments.  By default their arithmetic is plain numpy (set-up code must run without a
+GPU); with `device=<int>` the Euler-Maruyama loop / the observation noise run on the
+GPU (vgpa_make_trajectory, vgpa_collect_obs: the single-path view of the batched
+generators ensembles use, engine.make_trajectories / collect_observations) and give
+the same values (tests/test_gpu_datagen.py).
 """
 import numpy as np
 from numpy.random import SeedSequence, default_rng
@@ -63,7 +67,7 @@ class StochasticProcess(object):
     def rng(self):
         return self.rand_g
 
-    def collect_obs(self, n_obs, rn, h_mask=None):
+    def collect_obs(self, n_obs, rn, h_mask=None, device=None):
         """stochastic_process.py:130-230: equidistant noisy observations."""
         if self.tk is None or self.xt is None:
             raise NotImplementedError(f" {self.__class__.__name__}:"
@@ -83,11 +87,18 @@ class StochasticProcess(object):
         dim_d = 1 if obs_y.ndim == 1 else obs_y.shape[-1]
         if dim_d == 1:
             obs_noise = rn
-            obs_y += np.sqrt(obs_noise) * self.rand_g.standard_normal(dim_m)
+            xi = self.rand_g.standard_normal(dim_m)
+            if device is not None and not h_mask:
+                return obs_t, engine.collect_observations(self.xt, obs_t, [float(rn)], xi[None], device)[0], obs_noise
+            obs_y += np.sqrt(obs_noise) * xi
         else:
             obs_noise = np.diag(rn) if rn.ndim == 1 else rn * np.eye(dim_d)
             sq_rn = np.sqrt(obs_noise)
-            obs_y += sq_rn.dot(self.rand_g.standard_normal((dim_d, dim_m))).T
+            xi = self.rand_g.standard_normal((dim_d, dim_m))
+            if device is not None and not h_mask:
+                return obs_t, engine.collect_observations(self.xt, obs_t, np.diagonal(obs_noise), xi[None],
+                                                          device)[0], obs_noise
+            obs_y += sq_rn.dot(xi).T
         return obs_t, obs_y, obs_noise
 
     # -- the GPU stage ---------------------------------------------------------
@@ -151,15 +162,19 @@ class DoubleWell(_Scalar1D):
     """double_well.py:8-262"""
     model_key = "DW"
 
-    def make_trajectory(self, t0, tf, dt=0.01):
+    def make_trajectory(self, t0, tf, dt=0.01, device=None):
         tk = np.arange(t0, tf + dt, dt)
         dim_t = tk.size
         x = np.zeros(dim_t)
         x[0] = +self._theta if self.rng.random() > 0.5 else -self._theta
         x[0] += np.sqrt(0.5 * self._sigma * dt) * self.rng.standard_normal()
-        ek = np.sqrt(self._sigma * dt) * self.rng.standard_normal(dim_t)
-        for t in range(1, dim_t):
-            x[t] = x[t - 1] + 4.0 * x[t - 1] * (self._theta - x[t - 1] ** 2) * dt + ek[t]
+        z = self.rng.standard_normal(dim_t)
+        if device is not None:
+            x = engine.make_trajectories("DW", dim_t, dt, [self._theta], [self._sigma], z, [x[0]], device)[0]
+        else:
+            ek = np.sqrt(self._sigma * dt) * z
+            for t in range(1, dim_t):
+                x[t] = x[t - 1] + 4.0 * x[t - 1] * (self._theta - x[t - 1] ** 2) * dt + ek[t]
         self.sample_path = x
         self.time_window = tk
 
@@ -168,14 +183,18 @@ class OrnsteinUhlenbeck(_Scalar1D):
     """ornstein_uhlenbeck.py:8-234"""
     model_key = "OU"
 
-    def make_trajectory(self, t0, tf, dt=0.01, mu=0.0):
+    def make_trajectory(self, t0, tf, dt=0.01, mu=0.0, device=None):
         tk = np.arange(t0, tf + dt, dt)
         dim_t = tk.size
         x = np.zeros(dim_t)
         x[0] = mu
-        ek = np.sqrt(self._sigma * dt) * self.rng.standard_normal(dim_t)
-        for t in range(1, dim_t):
-            x[t] = x[t - 1] + self._theta * (mu - x[t - 1]) * dt + ek[t]
+        z = self.rng.standard_normal(dim_t)
+        if device is not None:
+            x = engine.make_trajectories("OU", dim_t, dt, [self._theta, mu], [self._sigma], z, [mu], device)[0]
+        else:
+            ek = np.sqrt(self._sigma * dt) * z
+            for t in range(1, dim_t):
+                x[t] = x[t - 1] + self._theta * (mu - x[t - 1]) * dt + ek[t]
         self.sample_path = x
         self.time_window = tk
 
@@ -228,14 +247,20 @@ class _VectorND(StochasticProcess):
     def inverse_sigma(self):
         return self.sig_inv
 
-    def _noise_path(self, dt, dim_t):
+    def _noise_path(self, dt, dim_t, z=None):
         # lorenz_63.py:203-219 / lorenz_96.py:289-302 (scipy's upper Cholesky factor)
         from scipy.linalg import cholesky, LinAlgError
         try:
             ek = cholesky(self._sigma * dt)
         except LinAlgError:
             ek = np.sqrt(np.eye(self.dim_d) * self._sigma * dt)
-        return ek.dot(self.rng.standard_normal((self.dim_d, dim_t))).T
+        return ek.dot(self.rng.standard_normal((self.dim_d, dim_t)) if z is None else z).T
+
+    def _gpu_path(self, dt, dim_t, device):
+        """The reference's burn-in and Euler-Maruyama loop on the GPU, fed with this object's own draws."""
+        z = self.rng.standard_normal((self.dim_d, dim_t))
+        return engine.make_trajectories(self.model_key, dim_t, dt, np.atleast_1d(self._theta), self._sigma_diag(),
+                                        z, None, device)[0]
 
 
 def _l63(state, u):
@@ -260,9 +285,12 @@ class Lorenz63(_VectorND):
         self._set_sigma(sigma)
         self._theta = np.asarray(theta, dtype=float)
 
-    def make_trajectory(self, t0, tf, dt=0.01):
+    def make_trajectory(self, t0, tf, dt=0.01, device=None):
         tk = np.arange(t0, tf + dt, dt)
         dim_t = tk.size
+        if device is not None:
+            self.sample_path, self.time_window = self._gpu_path(dt, dim_t, device), tk
+            return
         x0 = np.ones(3)
         delta_t = 1.0e-3
         for _ in range(5000):
@@ -291,9 +319,12 @@ class Lorenz96(_VectorND):
         self._set_sigma(sigma)
         self._theta = np.asarray(theta, dtype=float)
 
-    def make_trajectory(self, t0, tf, dt=0.01):
+    def make_trajectory(self, t0, tf, dt=0.01, device=None):
         tk = np.arange(t0, tf + dt, dt)
         dim_t = tk.size
+        if device is not None:
+            self.sample_path, self.time_window = self._gpu_path(dt, dim_t, device), tk
+            return
         x0 = self._theta * np.ones(self.dim_d)
         delta_t = 1.0e-3
         x0[int(self.dim_d / 2.0)] += delta_t

@@ -262,3 +262,67 @@ def obs_energy(obs_t, obs_y, R_diag, m, s, device=0, with_dr=False):
         return out + (dr,) if with_dr else out
     out = (float(E[0]), jm.reshape(N, D), js.reshape(N, D, D))
     return out + (dr.reshape(N, M, M),) if with_dr else out
+
+
+# -- batched data generation (host buffers) ------------------------------
+def _rows(a, B, n, name):
+    """(n,) shared by the B paths, or (B, n): returns the flat array and its row stride."""
+    a = f64(a).reshape(-1)
+    if a.size == n:
+        return a, 0
+    if a.size == B * n:
+        return a, n
+    raise ValueError(f"{name}: expected {n} or {B}x{n} values, got {a.size}")
+
+
+def make_trajectories(model, N, dt, theta, sigma_diag, z, x_init=None, device=0):
+    """B sample paths by the Euler-Maruyama loop of <Model>.make_trajectory, on the GPU.
+    z: (B, D, N) standard-normal draws in the reference's (D, N) layout ((B, N) for the 1-D models);
+    theta: DW [theta], OU [theta, mu], L63 [sigma, rho, beta], L96 [F]; x_init: state at t0 (required
+    for DW / OU; None for L63 / L96 = the reference's burn-in).  Returns (B, N, D) ((B, N) for D = 1)."""
+    key = str(model).upper()
+    if key not in MODELS:
+        raise ValueError(f" Unknown stochastic model -> {key}")
+    D = MODEL_DIM[key]
+    N = int(N)
+    z = f64(z)
+    if z.size % (N * D) or z.size == 0:
+        raise ValueError(f"z: expected B x {D} x {N} values, got {z.size}")
+    B = z.size // (N * D)
+    nth = {"DW": 1, "OU": 2, "L63": 3, "L96": 1}[key]
+    th, ths = _rows(theta, B, nth, "theta")
+    sg, sgs = _rows(sigma_diag, B, D, "sigma")
+    xi, xis = (None, 0) if x_init is None else _rows(x_init, B, D, "x_init")
+    path = np.empty((B, N) if D == 1 else (B, N, D))
+    rc = lib.vgpa_make_trajectory(device, MODELS[key], N, B, float(dt), th.ctypes.data, ths, sg.ctypes.data, sgs,
+                                  None if xi is None else xi.ctypes.data, xis, z.ctypes.data, N * D,
+                                  path.ctypes.data, N * D)
+    raise_for(rc, None)
+    return path
+
+
+def collect_observations(path, obs_t, R_diag, xi, device=0):
+    """B noisy observation sets (StochasticProcess.collect_obs) on the GPU.
+    path: (B, N, D) or (B, N), or one path shared by the sets ((N, D) / (N,) with xi giving B);
+    xi: (B, D, M) draws ((B, M) for D = 1).  Returns (B, M, D) ((B, M) for D = 1)."""
+    ot = np.ascontiguousarray(np.asarray(obs_t, dtype=np.int64).ravel())
+    M = ot.size
+    R = f64(np.atleast_1d(R_diag))
+    xi = f64(xi)
+    path = f64(path)
+    D = R.shape[-1]
+    if M == 0 or xi.size % (M * D):
+        raise ValueError(f"xi: expected B x {D} x {M} values, got {xi.size}")
+    B = xi.size // (M * D)
+    if path.ndim == (1 if D == 1 else 2):     # one path shared by the B sets
+        N, ps = path.shape[0], 0
+    elif path.ndim == (2 if D == 1 else 3) and path.shape[0] == B:
+        N, ps = path.shape[1], path.shape[1] * D
+    else:
+        raise ValueError(f"path: expected (N, D) or (B, N, D) with B = {B}, got {path.shape}")
+    Rr, Rs = _rows(R, B, D, "R")
+    out = np.empty((B, M) if D == 1 else (B, M, D))
+    rc = lib.vgpa_collect_obs(device, D, N, M, B, ot.ctypes.data, Rr.ctypes.data, Rs, path.ctypes.data, ps,
+                              xi.ctypes.data, M * D, out.ctypes.data, M * D)
+    raise_for(rc, None)
+    return out
