@@ -140,6 +140,11 @@ def cpu_port_rate(threads, problems, fam=None):
     return problems / el, el
 
 
+METRIC = "free-energy+grad evals/sec (L96 D=40, T=1000); batched problems/sec"
+WORKLOAD = ("L96 D=40 N=1001 (T=1000) RK2 ensemble: 8 obs sets x 32 starts x 16 noise values per GPU "
+            "(BASELINE configs[4])")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (the oracle port; the reference is
     Python and cannot travel to the box) on all host cores, same metric/config."""
@@ -156,12 +161,11 @@ def run_reference(args):
         el += cpu_port_rate(threads, per_step, fam)[1]
         n += per_step
     val = n / el
-    line = {"impl": "reference", "metric": "free-energy+grad evals/sec (L96 D=40, T=1000)", "value": val,
+    line = {"impl": "reference", "metric": METRIC, "value": val,
             "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "L96 D=40 N=1001 RK2 ensemble (BASELINE configs[4])",
-                       "problems_per_step": per_step},
+            "config": {"workload": WORKLOAD, "problems_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
                              "sample": f"{per_step} problems per step, one OpenMP thread each"},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -276,12 +280,11 @@ def run_b200(args):
                                    "frac_fp64": value / world * FLOP_EVAL / 1e12 / FP64_DMMA_TFLOPS,
                                    "gbs": value / world * BYTE_EVAL / 1e9,
                                    "frac_hbm": value / world * BYTE_EVAL / 1e9 / hbm_peak}}
-        line = {"metric": "free-energy+grad evals/sec (L96 D=40, T=1000); batched problems/sec",
+        line = {"metric": METRIC,
                 "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "L96 D=40 N=1001 (T=1000) RK2 ensemble: 8 obs sets x 32 starts x 16 "
-                                       "noise values per GPU (BASELINE configs[4])",
+                "config": {"workload": WORKLOAD,
                            "problems_per_gpu": B, "global_problems": B * world, "parallelism": f"dp{world}",
                            "l2": "inputs larger than L2 (x shard = %.1f GB)" % (B * N_X * 8 / 1e9),
                            "chunk": ev.chunk_size},
