@@ -10,6 +10,7 @@ Run (authoring container only):
     python tests/golden/make_golden.py            # per-evaluation fixtures
     python tests/golden/make_golden.py --scg      # + SCG convergence traces
     python tests/golden/make_golden.py --l96-full # + L96 N=1001 known answers
+    python tests/golden/make_golden.py --no-eval --scg-full   # full SCG runs at the BASELINE shapes
 
 What is recorded per case (all float64, reference layouts):
   inputs : model, method, D, N, dt, theta, sigma(diag), obs_t, obs_y, R(diag),
@@ -205,6 +206,32 @@ def make_scg(ref, which):
         print(f"{name.name}: it={n} fx={fx:.12g} f_eval={st['f_eval']} ({el:.1f}s)")
 
 
+def make_scg_full(ref, which):
+    """Full SCG optimisations to convergence with the reference's own optimiser at the BASELINE
+    shapes: configs[3] (L96 D=40, tf=10 -> N=1001, RK2; about 18 minutes of CPU) and configs[2]
+    (L63, tf=20 -> N=2002, Heun as shipped; about 3 minutes).  Only the trace is stored."""
+    jobs = {"L96": ("rk2", 10.0), "L63": ("heun", 20.0)}
+    for key in which:
+        method, tf = jobs[key]
+        sim, vgpa = build(ref, config(key, method, tf))
+        opts = {"max_it": 500, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False}
+        scg = ref["SCG"](vgpa.free_energy, vgpa.gradient, opts)
+        x0 = vgpa.initialization()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            x, fx = scg(x0.copy())
+        el = time.perf_counter() - t0
+        st = scg.stats
+        n = int(st["MaxIt"])
+        name = HERE / f"scg_{key}_full.npz"
+        np.savez_compressed(name, model=key, method=method, tf=np.float64(tf), max_it=np.int64(500),
+                            n_it=np.int64(n), fx_final=np.float64(fx), trace_fx=st["fx"][:n].copy(),
+                            trace_dfx=st["dfx"][:n].copy(), trace_beta=st["beta"][:n].copy(),
+                            f_eval=np.float64(st["f_eval"]), df_eval=np.float64(st["df_eval"]),
+                            ref_seconds=np.float64(el))
+        print(f"{name.name}: it={n} fx={fx:.12g} f_eval={st['f_eval']} ({el:.1f}s)")
+
+
 def make_scg_rosenbrock(ref):
     """The reference's SCG on an analytic test function (no VGPA involved): pins the
     repo's own optimiser (vgpa_b200/scg.py) on the CPU."""
@@ -260,6 +287,8 @@ if __name__ == "__main__":
     ap.add_argument("--l96-full", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--rosenbrock", action="store_true")
+    ap.add_argument("--scg-full", nargs="*", default=None,
+                    help="full SCG runs at the BASELINE shapes (default: L63 L96; ~20 min of CPU)")
     a = ap.parse_args()
     ref = _import_reference()
     if not a.no_eval:
@@ -270,4 +299,6 @@ if __name__ == "__main__":
         make_l96_full(ref)
     if a.rosenbrock:
         make_scg_rosenbrock(ref)
+    if a.scg_full is not None:
+        make_scg_full(ref, a.scg_full or ["L63", "L96"])
     print(json.dumps({"numpy": np.__version__}))

@@ -45,6 +45,29 @@ def test_scg_trace_matches_reference(model):
     vgpa.close()
 
 
+@pytest.mark.parametrize("model", ["L63", "L96"])
+def test_full_scg_optimisation_matches_reference(model):
+    """BASELINE configs[3] (L96 D=40, T=1000, RK2) and configs[2] (L63, T=2000, Heun as shipped): the
+    whole SCG optimisation to convergence, against the trace the unmodified reference produced
+    (scg_<model>_full.npz; 18 and 3 minutes of CPU there, about a second here)."""
+    from vgpa_b200 import SCG, Simulation
+    g = np.load(GOLDEN / f"scg_{model}_full.npz")
+    sim = Simulation("t")
+    sim.setup(mg.config(model, str(g["method"]), float(g["tf"])))
+    vgpa = sim.build()
+    x0 = vgpa.initialization()
+    scg = SCG(vgpa.free_energy, vgpa.gradient,
+              {"max_it": int(g["max_it"]), "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False})
+    x, fx = scg(x0.copy())
+    n_ref, n_new = int(g["n_it"]), int(scg.stats["MaxIt"])
+    n = min(n_ref, n_new)
+    assert abs(n_ref - n_new) <= max(2, n_ref // 50), (n_ref, n_new)
+    ref, new = g["trace_fx"][:n], scg.stats["fx"][:n]
+    assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6
+    assert abs(fx - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0)
+    vgpa.close()
+
+
 def test_l96_north_star_known_answers():
     """L96 D=40, tf=10 (N=1001, T=1000 steps), RK2: F(x0), |grad|, gradient samples."""
     from vgpa_b200 import Simulation
