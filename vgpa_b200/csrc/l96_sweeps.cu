@@ -195,7 +195,12 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     double bc = bo[irow], bn = 0.0;
     __syncthreads();
 
+    const bool small_launch = gridDim.x <= SMALL_LAUNCH;
     for (int k = 0; k < N - 1; ++k) {
+        // launches of at most one CTA per SM (a single SCG run) have nothing to hide the DRAM latency of
+        // their only input stream behind: pull this warp's eight rows of A into L2, PF_STEPS indices ahead
+        if (small_launch && lane == 0 && k + 1 + PF_STEPS < N)
+            bulk_prefetch_l2(A + (long long)(k + 1 + PF_STEPS) * D * D + (long long)(8 * w) * D, 8 * ROWB);
         // A(k+1), b(k+1) for this step's later stages: loads stay in flight during stage 0
         {
             const double* an = arow + (long long)(k + 1) * D * D;
