@@ -112,3 +112,45 @@ def test_reference_operator_objects_on_gpu():
     assert rel_err(lam, g["lamt"]) < 1e-9 and rel_err(psi, g["psit"]) < 1e-9
     assert abs(vgpa.free_energy(x) - F) <= 1e-9 * abs(F)
     vgpa.close()
+
+
+def test_gradient_arrays_are_owned_by_the_caller():
+    """VarGP.gradient returns the page-locked buffer the device copy landed in, without a copy; a
+    buffer is reused only when the caller has dropped every reference to it (optim_scg.py keeps the
+    last two gradients alive and expects them to stay intact)."""
+    from vgpa_b200 import Simulation
+    sim = Simulation("t")
+    sim.setup(mg.config("L63", "rk2", 2.0))
+    vgpa = sim.build()
+    x0 = vgpa.initialization()
+    rng = np.random.default_rng(0)
+    xs = [x0 * (1.0 + 1e-3 * rng.uniform(-1, 1, x0.size)) for _ in range(6)]
+    held, copies = [], []
+    for x in xs[:4]:                     # hold four gradients alive across later evaluations
+        vgpa.free_energy(x)
+        g = vgpa.gradient(x)
+        held.append(g)
+        copies.append(g.copy())
+    assert len({id(g) for g in held}) == 4
+    for g, c in zip(held, copies):
+        assert np.array_equal(g, c)
+    # the same x again: an equal but distinct array (the first one is the caller's, even if modified)
+    held[3] *= 2.0
+    again = vgpa.gradient(xs[3])
+    assert again is not held[3] and np.array_equal(again, copies[3])
+    # dropping references lets buffers be reused: the pool stays small over many evaluations
+    del held, again, g
+    n_buffers = len(vgpa._pin[1]._arrs)
+    for k in range(24):
+        x = xs[k % 6] * (1.0 + 1e-6 * k)
+        vgpa.free_energy(x)
+        last = vgpa.gradient(x)
+    assert len(vgpa._pin[1]._arrs) == n_buffers
+    # more gradients alive than the pool holds: still correct (copies out of a private buffer)
+    many = [vgpa.gradient(x * (1.0 + 1e-5 * k)) for k in range(12)]
+    ref = vgpa.gradient(x * (1.0 + 1e-5 * 11))
+    assert np.array_equal(many[11], ref) and len({id(m) for m in many}) == 12
+    # closing the object must not pull the memory from under arrays the caller still holds
+    keep = last.copy()
+    vgpa.close()
+    assert np.array_equal(last, keep) and np.array_equal(many[0], many[0].copy())

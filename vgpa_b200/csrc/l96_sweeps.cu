@@ -449,7 +449,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
         // Small launches only (at most one CTA per SM: nothing else hides HBM latency, which is what a
         // single problem then waits for): this warp's eight rows of the three streams, PF_STEPS
         // indices ahead, into L2.  With full waves the same prefetch was measured harmful (evictions);
-        // in the forward sweep it does not pay even for one problem.
+        // the forward sweep does the same for its single stream.
         if (small_launch && lane == 0 && t >= PF_STEPS) {
             const long long o = (long long)(t - PF_STEPS) * D * D + (long long)(8 * w) * D;
             bulk_prefetch_l2(A + o, 8 * ROWB);

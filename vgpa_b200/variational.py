@@ -8,11 +8,54 @@ ONE batched CUDA evaluation (B = 1 here) through the C ABI; the gradient of the
 last x is cached so that `f(x)` followed by `df(x)` costs one evaluation instead
 of the reference's two.  There is no CPU path.
 """
+import ctypes as C
+import sys
+
 import numpy as np
 from scipy.interpolate import CubicSpline
 
-from ._lib import PinnedArray
+from ._lib import PinnedArray, lib
 from .engine import BatchEvaluator
+
+_STILL_REFERENCED = []   # page-locked gradient buffers a caller still held when their VarGP was closed
+
+
+class _GradientPool:
+    """Page-locked buffers for the gradient, handed to the caller WITHOUT a copy.
+
+    `VarGP.gradient` must return an array the caller owns (optim_scg.py keeps the last two
+    gradients alive).  Copying 13 MB out of a staging buffer and first-touching a fresh
+    allocation costs about 2 ms per call at the L96 shape, so the device-to-host copy lands
+    directly in the array that is returned, and a buffer is reused only when no reference to it
+    is left outside the pool (the root array of each buffer is what the caller receives, so
+    every outside reference and every view shows in its reference count)."""
+
+    def __init__(self, n, max_buffers=8):
+        self.n, self.max_buffers = int(n), int(max_buffers)
+        self._arrs, self._ptrs = [], []
+
+    def take(self):
+        for i in range(len(self._arrs)):
+            if sys.getrefcount(self._arrs[i]) == 2:      # the list + getrefcount's argument
+                return self._arrs[i]
+        if len(self._arrs) >= self.max_buffers:
+            return None                                   # caller hoards gradients: fall back to copies
+        ptr = lib.vgpa_host_alloc(max(self.n, 1) * 8)
+        if not ptr:
+            return None
+        buf = (C.c_double * max(self.n, 1)).from_address(ptr)
+        self._arrs.append(np.frombuffer(buf, dtype=np.float64, count=self.n))
+        self._ptrs.append(ptr)
+        return self._arrs[-1]
+
+    def close(self):
+        while self._arrs:
+            arr, ptr = self._arrs.pop(), self._ptrs.pop()
+            if sys.getrefcount(arr) == 2:                 # the local name + getrefcount's argument
+                del arr
+                lib.vgpa_host_free(ptr)
+            else:                                         # still in use outside: never free under it
+                _STILL_REFERENCED.append((arr, ptr))
 
 
 def _diag(a, what):
@@ -49,6 +92,7 @@ class VarGP(object):
         self._g_cached = None
         self._full_for = None
         self._pin = None
+        self._g_owned = False
         self.n_eval = 0
 
     @property
@@ -107,20 +151,25 @@ class VarGP(object):
         first-touch page faults of a fresh 13 MB array per call)."""
         ev = self._ev
         if self._pin is None:
-            self._pin = (PinnedArray((ev.n_x,)), PinnedArray((1, ev.n_x)), np.empty(1))
-        px, pg, F = self._pin[0].array, self._pin[1].array, self._pin[2]
+            self._pin = (PinnedArray((ev.n_x,)), _GradientPool(ev.n_x), np.empty(1))
+        px, pool, F = self._pin[0].array, self._pin[1], self._pin[2]
         xa = np.asarray(x).reshape(-1)
         if xa.size != ev.n_x:
             raise ValueError(f"x: expected {ev.n_x} values, got {xa.size}")
         self._x_cached = None                   # px is about to change
+        self._g_cached = None                   # ... and our reference must not keep a buffer busy
+        g = pool.take()
+        self._g_owned = g is not None           # the caller may receive this very array, once
+        if g is None:
+            g = np.empty(ev.n_x)
         np.copyto(px, xa)
-        ev.eval(px, want_grad=True, F_out=F, G_out=pg)
+        ev.eval(px, want_grad=True, F_out=F, G_out=g.reshape(1, -1))
         self.n_eval += 1
         self._x_cached = px
         self._x_obj = x                         # the caller's array object (identity shortcut below)
         self._x_probe = px[::self._probe_step(px.size)].copy()
         self._f_cached = float(F[0])
-        self._g_cached = pg[0]
+        self._g_cached = g
         self._full_for = None
 
     @staticmethod
@@ -152,9 +201,14 @@ class VarGP(object):
     def gradient(self, x, eval_fun=False):
         """[dL/dA | dL/db] (variational.py:202-289).  `eval_fun=True` asks for a
         consistent state at a new x; the cache makes that automatic."""
-        if not self._is_cached(x):
+        if not self._is_cached(x) or self._g_cached is None:
             self._evaluate(x)
-        return self._g_cached.copy()
+        if self._g_owned:
+            # hand the page-locked buffer over: from here on it is the caller's array (it may even be
+            # modified in place), so this object forgets it; asking again at the same x re-evaluates
+            g, self._g_cached, self._g_owned = self._g_cached, None, False
+            return g
+        return self._g_cached.copy()            # pool exhausted: private buffer, copies out
 
     @property
     def arg_out(self):
@@ -172,6 +226,6 @@ class VarGP(object):
             self._ev_obj = None
         if self._pin is not None:
             self._x_cached = self._g_cached = None
-            for a in self._pin[:2]:
-                a.free()
+            self._pin[0].free()
+            self._pin[1].close()
             self._pin = None
