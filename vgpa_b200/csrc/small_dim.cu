@@ -109,6 +109,73 @@ constexpr int PF_AHEAD = 16;   // time indices of look-ahead for the L2 prefetch
 // (measured: OU x 65536 5.1 -> 10.2 ms with prefetching, L63 x 4096 7.3 -> 5.7 ms).
 constexpr int PF_MAX_BATCH = 8192;
 
+// one step k -> k+1 of solve_fwd (the four solver files): Ak, bk at index k, An, bn at index k+1
+template <int D, int METHOD>
+__device__ __forceinline__ void fwd_step(const double* m, const double* S, const double* Ak, const double* bk,
+                                         const double* An, const double* bn, const double* sig, double dt,
+                                         double* mn, double* Sn)
+{
+    constexpr int DD = D * D;
+    const double h = 0.5 * dt;
+    (void)h; (void)An; (void)bn;
+    if (METHOD == ODE_EULER) {  // euler.py:84-87
+        double v1[D], k1[DD];
+        fun_m<D>(m, Ak, bk, v1);
+        axpy<D>(m, dt, v1, mn);
+        fun_S<D>(S, Ak, sig, k1);
+        axpy<DD>(S, dt, k1, Sn);
+    } else if (METHOD == ODE_HEUN) {  // heun.py:91-106
+        double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+        fun_m<D>(m, Ak, bk, v1);
+        axpy<D>(m, dt, v1, vt);
+        fun_m<D>(vt, An, bn, v2);
+#pragma unroll
+        for (int i = 0; i < D; ++i) mn[i] = m[i] + h * (v1[i] + v2[i]);
+        fun_S<D>(S, Ak, sig, k1);
+        axpy<DD>(S, dt, k1, tmp);
+        fun_S<D>(tmp, An, sig, k2);
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Sn[i] = S[i] + h * (k1[i] + k2[i]);
+    } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:92,96 (inner stage: S in place of A)
+        double am[DD], bm[D], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+        mid<DD>(Ak, An, am);
+        mid<D>(bk, bn, bm);
+        fun_m<D>(m, Ak, bk, v1);
+        axpy<D>(m, h, v1, vt);
+        fun_m<D>(vt, am, bm, v2);
+        axpy<D>(m, dt, v2, mn);
+        fun_S<D>(S, S, sig, k1);
+        axpy<DD>(S, h, k1, tmp);
+        fun_S<D>(tmp, am, sig, k2);
+        axpy<DD>(S, dt, k2, Sn);
+    } else {  // runge_kutta4.py:93-108
+        double am[DD], bm[D], v1[D], v2[D], v3[D], v4[D], vt[D];
+        double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
+        mid<DD>(Ak, An, am);
+        mid<D>(bk, bn, bm);
+        fun_m<D>(m, Ak, bk, v1);
+        axpy<D>(m, h, v1, vt);
+        fun_m<D>(vt, am, bm, v2);
+        axpy<D>(m, h, v2, vt);
+        fun_m<D>(vt, am, bm, v3);
+        axpy<D>(m, dt, v3, vt);
+        fun_m<D>(vt, An, bn, v4);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            mn[i] = m[i] + dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0;
+        fun_S<D>(S, Ak, sig, k1);
+        axpy<DD>(S, h, k1, tmp);
+        fun_S<D>(tmp, am, sig, k2);
+        axpy<DD>(S, h, k2, tmp);
+        fun_S<D>(tmp, am, sig, k3);
+        axpy<DD>(S, dt, k3, tmp);
+        fun_S<D>(tmp, An, sig, k4);
+#pragma unroll
+        for (int i = 0; i < DD; ++i)
+            Sn[i] = S[i] + dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // forward sweep: one thread per problem
 // ---------------------------------------------------------------------------
@@ -154,62 +221,7 @@ small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
             }
         }
         double mn[D], Sn[DD];
-        if (METHOD == ODE_EULER) {  // euler.py:84-87
-            double v1[D], k1[DD];
-            fun_m<D>(m, Ak, bk, v1);
-            axpy<D>(m, dt, v1, mn);
-            fun_S<D>(S, Ak, sig, k1);
-            axpy<DD>(S, dt, k1, Sn);
-        } else if (METHOD == ODE_HEUN) {  // heun.py:91-106
-            double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
-            fun_m<D>(m, Ak, bk, v1);
-            axpy<D>(m, dt, v1, vt);
-            fun_m<D>(vt, An, bn, v2);
-#pragma unroll
-            for (int i = 0; i < D; ++i) mn[i] = m[i] + h * (v1[i] + v2[i]);
-            fun_S<D>(S, Ak, sig, k1);
-            axpy<DD>(S, dt, k1, tmp);
-            fun_S<D>(tmp, An, sig, k2);
-#pragma unroll
-            for (int i = 0; i < DD; ++i) Sn[i] = S[i] + h * (k1[i] + k2[i]);
-        } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:92,96 (inner stage: S in place of A)
-            double am[DD], bm[D], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
-            mid<DD>(Ak, An, am);
-            mid<D>(bk, bn, bm);
-            fun_m<D>(m, Ak, bk, v1);
-            axpy<D>(m, h, v1, vt);
-            fun_m<D>(vt, am, bm, v2);
-            axpy<D>(m, dt, v2, mn);
-            fun_S<D>(S, S, sig, k1);
-            axpy<DD>(S, h, k1, tmp);
-            fun_S<D>(tmp, am, sig, k2);
-            axpy<DD>(S, dt, k2, Sn);
-        } else {  // runge_kutta4.py:93-108
-            double am[DD], bm[D], v1[D], v2[D], v3[D], v4[D], vt[D];
-            double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
-            mid<DD>(Ak, An, am);
-            mid<D>(bk, bn, bm);
-            fun_m<D>(m, Ak, bk, v1);
-            axpy<D>(m, h, v1, vt);
-            fun_m<D>(vt, am, bm, v2);
-            axpy<D>(m, h, v2, vt);
-            fun_m<D>(vt, am, bm, v3);
-            axpy<D>(m, dt, v3, vt);
-            fun_m<D>(vt, An, bn, v4);
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                mn[i] = m[i] + dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0;
-            fun_S<D>(S, Ak, sig, k1);
-            axpy<DD>(S, h, k1, tmp);
-            fun_S<D>(tmp, am, sig, k2);
-            axpy<DD>(S, h, k2, tmp);
-            fun_S<D>(tmp, am, sig, k3);
-            axpy<DD>(S, dt, k3, tmp);
-            fun_S<D>(tmp, An, sig, k4);
-#pragma unroll
-            for (int i = 0; i < DD; ++i)
-                Sn[i] = S[i] + dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
-        }
+        fwd_step<D, METHOD>(m, S, Ak, bk, An, bn, sig, dt, mn, Sn);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             m[i] = mn[i];
@@ -225,6 +237,156 @@ small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
             st[(long long)(k + 1) * DD + i] = Sn[i];
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// staged forward sweep (large batches)
+// ---------------------------------------------------------------------------
+// One thread per problem as above, but with one thread per problem every global access of a warp
+// touches 32 different lines (problems are N * D * (D + 1) doubles apart).  With tens of thousands
+// of problems in flight that is what bounds the forward sweep (the L2 look-ahead of the small-batch
+// kernel cannot be used: its lines are evicted before use).  Here a warp moves the streams of its 32
+// problems through shared memory a block of TB time indices at a time.  A problem's block is
+// contiguous in HBM, so the warp fetches it with coalesced 8-byte cp.async copies (lane e: element e
+// of problem j's block, all copies of a block in flight at once) into row j of a buffer whose row
+// pitch is odd (lane j then walks its own row without bank conflicts); m(t), S(t) take the same road
+// back.  Measured (B200, F + gradient, forward sweep only): L63 x 16384 3.2 -> 1.8 ms, OU x 65536
+// 1.98 -> 1.20 ms.  For batches of a few thousand problems (latency bound, not request bound) it is
+// no faster (L63 x 4096: 1.64 vs 1.60 ms; OU x 1024: 0.51 vs 0.25 ms), and the same treatment of the
+// backward sweep (six input streams, two output streams) was slower at every size tried (L63 x 4096
+// 3.6 -> 4.7 ms, x 16384 6.3 -> 10.1 ms, OU x 65536 2.5 -> 2.9 ms): both stay on the register-prefetch
+// kernels (profiles/README.md).
+__host__ __device__ constexpr int odd_pitch(int n) { return n | 1; }
+
+// 8-byte asynchronous global -> shared copy (SASS LDGSTS): no register, no scoreboard, so a warp has all
+// the copies of a block in flight at once; waited for with stage_wait()
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void stage_wait()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+}
+// rows j = 0 .. nprob-1 of len <= MAXLEN doubles: problem j at g + j * gstride <-> row j of buf
+template <int MAXLEN>
+__device__ __forceinline__ void stage_in(double* __restrict__ buf, int pitch, const double* __restrict__ g,
+                                         long long gstride, int nprob, int len, int lane)
+{
+    for (int j = 0; j < nprob; ++j) {
+        const double* src = g + (long long)j * gstride;
+        double* dst = buf + j * pitch;
+#pragma unroll
+        for (int it = 0; it < (MAXLEN + 31) / 32; ++it) {
+            const int e = lane + 32 * it;
+            if (e < len) cp_async8(dst + e, src + e);
+        }
+    }
+}
+template <int MAXLEN>
+__device__ __forceinline__ void stage_out(const double* __restrict__ buf, int pitch, double* __restrict__ g,
+                                          long long gstride, int nprob, int len, int lane)
+{
+#pragma unroll 4
+    for (int j = 0; j < nprob; ++j) {
+        double* dst = g + (long long)j * gstride;
+        const double* src = buf + j * pitch;
+#pragma unroll
+        for (int it = 0; it < (MAXLEN + 31) / 32; ++it) {
+            const int e = lane + 32 * it;
+            if (e < len) dst[e] = src[e];
+        }
+    }
+}
+// lines [p, p + bytes) into L2
+__device__ __forceinline__ void prefetch_span(const double* p, int bytes)
+{
+    const char* c = reinterpret_cast<const char*>(p);
+    for (int o = 0; o < bytes; o += 128) prefetch_l2(c + o);
+    if (bytes > 0) prefetch_l2(c + bytes - 8);
+}
+
+template <int D, int METHOD, int TB>
+__global__ void __launch_bounds__(32)
+small_fwd_staged_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count)
+{
+    constexpr int DD = D * D, NI = TB + 1;
+    constexpr int PA = odd_pitch(NI * DD), PB = odd_pitch(NI * D), PS = odd_pitch(TB * DD), PM = odd_pitch(TB * D);
+    extern __shared__ double stage_smem[];
+    double* sA = stage_smem;
+    double* sB = sA + 32 * PA;
+    double* sS = sB + 32 * PB;
+    double* sM = sS + 32 * PS;
+    const int lane = threadIdx.x, lp0 = blockIdx.x * 32;
+    const int nprob = min(32, count - lp0);
+    const bool on = lane < nprob;
+    const int lp = lp0 + (on ? lane : 0), p = p0 + lp, N = b.N;
+    const double* A0 = x + (long long)(p0 + lp0) * xs;      // problem 0 of this warp
+    const double* b0 = A0 + (long long)N * DD;
+    double* mt0 = s.mt + (long long)lp0 * N * D;
+    double* st0 = s.st + (long long)lp0 * N * DD;
+    double sig[D], m[D], S[DD];
+    ld_vec<D>(b.sigma + p * b.sigma_stride, sig);
+    ld_vec<D>(b.m0 + p * b.m0_stride, m);
+    ld_vec<DD>(b.s0 + p * b.s0_stride, S);
+    if (on) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) mt0[(long long)lane * N * D + i] = m[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) st0[(long long)lane * N * DD + i] = S[i];
+    }
+    const double dt = b.dt;
+    for (int k0 = 0; k0 < N - 1; k0 += TB) {
+        const int nb = min(TB, N - 1 - k0);      // steps k0 .. k0 + nb - 1 read indices k0 .. k0 + nb
+        stage_in<NI * DD>(sA, PA, A0 + (long long)k0 * DD, xs, nprob, (nb + 1) * DD, lane);
+        stage_in<NI * D>(sB, PB, b0 + (long long)k0 * D, xs, nprob, (nb + 1) * D, lane);
+        if (on && k0 + TB < N - 1) {
+            const int nn = min(TB, N - 1 - (k0 + TB)) + 1;
+            prefetch_span(A0 + (long long)lane * xs + (long long)(k0 + TB) * DD, nn * DD * 8);
+            prefetch_span(b0 + (long long)lane * xs + (long long)(k0 + TB) * D, nn * D * 8);
+        }
+        stage_wait();
+        if (on) {
+            const double* ra = sA + lane * PA;
+            const double* rb = sB + lane * PB;
+            double* rs = sS + lane * PS;
+            double* rm = sM + lane * PM;
+            for (int kk = 0; kk < nb; ++kk) {
+                double Ak[DD], An[DD], bk[D], bn[D], mn[D], Sn[DD];
+#pragma unroll
+                for (int i = 0; i < DD; ++i) {
+                    Ak[i] = ra[kk * DD + i];
+                    An[i] = ra[(kk + 1) * DD + i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    bk[i] = rb[kk * D + i];
+                    bn[i] = rb[(kk + 1) * D + i];
+                }
+                fwd_step<D, METHOD>(m, S, Ak, bk, An, bn, sig, dt, mn, Sn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    m[i] = mn[i];
+                    rm[kk * D + i] = mn[i];
+                }
+#pragma unroll
+                for (int i = 0; i < DD; ++i) {
+                    S[i] = Sn[i];
+                    rs[kk * DD + i] = Sn[i];
+                }
+            }
+        }
+        __syncwarp();
+        stage_out<TB * DD>(sS, PS, st0 + (long long)(k0 + 1) * DD, (long long)N * DD, nprob, nb * DD, lane);
+        stage_out<TB * D>(sM, PM, mt0 + (long long)(k0 + 1) * D, (long long)N * D, nprob, nb * D, lane);
+        __syncwarp();
+    }
+}
+template <int D, int TB> constexpr size_t fwd_stage_bytes()
+{
+    return sizeof(double) * 32 * (odd_pitch((TB + 1) * D * D) + odd_pitch((TB + 1) * D) + odd_pitch(TB * D * D) + odd_pitch(TB * D));
 }
 
 // ---------------------------------------------------------------------------
@@ -433,6 +595,79 @@ __device__ __forceinline__ void grad_at(const double* th, const double* isg, dou
     }
 }
 
+// one step t -> t-1 of solve_bwd: (At, gt, Gt) at index t, (Am, gm, Gm) at index t-1; jm = jump of lambda
+template <int D, int METHOD>
+__device__ __forceinline__ void bwd_step(const double* lam, const double* Psi, const double* At, const double* gt,
+                                         const double* Gt, const double* Am, const double* gm, const double* Gm,
+                                         const double* jm, double dt, double* ln, double* Pn)
+{
+    constexpr int DD = D * D;
+    const double h = 0.5 * dt;
+    (void)h; (void)Am; (void)gm; (void)Gm;
+    if (METHOD == ODE_EULER) {  // euler.py:146-149
+        double v1[D], k1[DD];
+        fun_lam<D>(gt, At, lam, v1);
+        fun_psi<D>(Gt, At, Psi, k1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) ln[i] = lam[i] - v1[i] * dt + jm[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - k1[i] * dt;
+    } else if (METHOD == ODE_HEUN) {  // heun.py:170-185
+        double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+        fun_lam<D>(gt, At, lam, v1);
+        axpy<D>(lam, -dt, v1, vt);
+        fun_lam<D>(gm, Am, vt, v2);
+        fun_psi<D>(Gt, At, Psi, k1);
+        axpy<DD>(Psi, -dt, k1, tmp);
+        fun_psi<D>(Gm, Am, tmp, k2);
+#pragma unroll
+        for (int i = 0; i < D; ++i) ln[i] = lam[i] - h * (v1[i] + v2[i]) + jm[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - h * (k1[i] + k2[i]);
+    } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:180-189
+        double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
+        mid<DD>(Am, At, am);
+        mid<D>(gm, gt, gmid);
+        mid<DD>(Gm, Gt, Gmid);
+        fun_lam<D>(gt, At, lam, v1);
+        axpy<D>(lam, -h, v1, vt);
+        fun_lam<D>(gmid, am, vt, v2);
+        fun_psi<D>(Gt, At, Psi, k1);
+        axpy<DD>(Psi, -h, k1, tmp);
+        fun_psi<D>(Gmid, am, tmp, k2);
+#pragma unroll
+        for (int i = 0; i < D; ++i) ln[i] = lam[i] - dt * v2[i] + jm[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - dt * k2[i];
+    } else {  // runge_kutta4.py:191-206
+        double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], v3[D], v4[D], vt[D];
+        double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
+        mid<DD>(Am, At, am);
+        mid<D>(gm, gt, gmid);
+        mid<DD>(Gm, Gt, Gmid);
+        fun_lam<D>(gt, At, lam, v1);
+        axpy<D>(lam, -h, v1, vt);
+        fun_lam<D>(gmid, am, vt, v2);
+        axpy<D>(lam, -h, v2, vt);
+        fun_lam<D>(gmid, am, vt, v3);
+        axpy<D>(lam, -dt, v3, vt);
+        fun_lam<D>(gm, Am, vt, v4);
+        fun_psi<D>(Gt, At, Psi, k1);
+        axpy<DD>(Psi, -h, k1, tmp);
+        fun_psi<D>(Gmid, am, tmp, k2);
+        axpy<DD>(Psi, -h, k2, tmp);
+        fun_psi<D>(Gmid, am, tmp, k3);
+        axpy<DD>(Psi, -dt, k3, tmp);
+        fun_psi<D>(Gm, Am, tmp, k4);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            ln[i] = lam[i] - dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0 + jm[i];
+#pragma unroll
+        for (int i = 0; i < DD; ++i)
+            Pn[i] = Psi[i] - dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
+    }
+}
+
 // jm_dense / js_dense: dense jump tables of the stand-alone sweep (BwdOde.__call__,
 // bwd_ode.py:45); null in the batched path, where the jumps come from the observations.
 struct SmallBwdArgs {
@@ -547,68 +782,7 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
             }
         }
         double ln[D], Pn[DD];
-        if (METHOD == ODE_EULER) {  // euler.py:146-149
-            double v1[D], k1[DD];
-            fun_lam<D>(gt, At, lam, v1);
-            fun_psi<D>(Gt, At, Psi, k1);
-#pragma unroll
-            for (int i = 0; i < D; ++i) ln[i] = lam[i] - v1[i] * dt + jm[i];
-#pragma unroll
-            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - k1[i] * dt;
-        } else if (METHOD == ODE_HEUN) {  // heun.py:170-185
-            double v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
-            fun_lam<D>(gt, At, lam, v1);
-            axpy<D>(lam, -dt, v1, vt);
-            fun_lam<D>(gm, Am, vt, v2);
-            fun_psi<D>(Gt, At, Psi, k1);
-            axpy<DD>(Psi, -dt, k1, tmp);
-            fun_psi<D>(Gm, Am, tmp, k2);
-#pragma unroll
-            for (int i = 0; i < D; ++i) ln[i] = lam[i] - h * (v1[i] + v2[i]) + jm[i];
-#pragma unroll
-            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - h * (k1[i] + k2[i]);
-        } else if (METHOD == ODE_RK2) {  // runge_kutta2.py:180-189
-            double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], vt[D], k1[DD], k2[DD], tmp[DD];
-            mid<DD>(Am, At, am);
-            mid<D>(gm, gt, gmid);
-            mid<DD>(Gm, Gt, Gmid);
-            fun_lam<D>(gt, At, lam, v1);
-            axpy<D>(lam, -h, v1, vt);
-            fun_lam<D>(gmid, am, vt, v2);
-            fun_psi<D>(Gt, At, Psi, k1);
-            axpy<DD>(Psi, -h, k1, tmp);
-            fun_psi<D>(Gmid, am, tmp, k2);
-#pragma unroll
-            for (int i = 0; i < D; ++i) ln[i] = lam[i] - dt * v2[i] + jm[i];
-#pragma unroll
-            for (int i = 0; i < DD; ++i) Pn[i] = Psi[i] - dt * k2[i];
-        } else {  // runge_kutta4.py:191-206
-            double am[DD], gmid[D], Gmid[DD], v1[D], v2[D], v3[D], v4[D], vt[D];
-            double k1[DD], k2[DD], k3[DD], k4[DD], tmp[DD];
-            mid<DD>(Am, At, am);
-            mid<D>(gm, gt, gmid);
-            mid<DD>(Gm, Gt, Gmid);
-            fun_lam<D>(gt, At, lam, v1);
-            axpy<D>(lam, -h, v1, vt);
-            fun_lam<D>(gmid, am, vt, v2);
-            axpy<D>(lam, -h, v2, vt);
-            fun_lam<D>(gmid, am, vt, v3);
-            axpy<D>(lam, -dt, v3, vt);
-            fun_lam<D>(gm, Am, vt, v4);
-            fun_psi<D>(Gt, At, Psi, k1);
-            axpy<DD>(Psi, -h, k1, tmp);
-            fun_psi<D>(Gmid, am, tmp, k2);
-            axpy<DD>(Psi, -h, k2, tmp);
-            fun_psi<D>(Gmid, am, tmp, k3);
-            axpy<DD>(Psi, -dt, k3, tmp);
-            fun_psi<D>(Gm, Am, tmp, k4);
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                ln[i] = lam[i] - dt * (v1[i] + 2.0 * (v2[i] + v3[i]) + v4[i]) / 6.0 + jm[i];
-#pragma unroll
-            for (int i = 0; i < DD; ++i)
-                Pn[i] = Psi[i] - dt * (k1[i] + 2.0 * (k2[i] + k3[i]) + k4[i]) / 6.0;
-        }
+        bwd_step<D, METHOD>(lam, Psi, At, gt, Gt, Am, gm, Gm, jm, dt, ln, Pn);
 #pragma unroll
         for (int i = 0; i < D; ++i) Pn[i * D + i] += js[i];
         if (dense) {
@@ -713,6 +887,24 @@ template <int D>
 static void fwd_dispatch(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
                          int count, cudaStream_t st)
 {
+    if (count > PF_MAX_BATCH) {   // large batches: streams staged through shared memory, one warp per CTA
+        constexpr int TB = (D == 1) ? 16 : 8;
+        const size_t sh = fwd_stage_bytes<D, TB>();
+        const int bl = (count + 31) / 32;
+#define VGPA_FWD_STAGED(M)                                                                              \
+    do {                                                                                                \
+        cudaFuncSetAttribute(small_fwd_staged_kernel<D, M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+        small_fwd_staged_kernel<D, M, TB><<<bl, 32, sh, st>>>(b, s, x, xs, p0, count);                  \
+    } while (0)
+        switch (b.method) {
+        case ODE_EULER: VGPA_FWD_STAGED(ODE_EULER); break;
+        case ODE_HEUN:  VGPA_FWD_STAGED(ODE_HEUN); break;
+        case ODE_RK2:   VGPA_FWD_STAGED(ODE_RK2); break;
+        default:        VGPA_FWD_STAGED(ODE_RK4); break;
+        }
+#undef VGPA_FWD_STAGED
+        return;
+    }
     // one thread per problem: small CTAs spread a small batch over more SMs (more load streams in flight)
     const int th = (count <= 148 * 64) ? 32 : 64, bl = (count + th - 1) / th;
     switch (b.method) {
