@@ -135,3 +135,40 @@ def test_small_models_at_full_size_match_oracle(oracle, model, method, N):
         Fo, Go = oracle.eval(prob, X[r])
         assert abs(F[r] - Fo) <= TOL * abs(Fo)
         assert rel_err(G[r], Go) < TOL
+
+
+@pytest.mark.parametrize("model,method,N", [("L63", "rk2", 61), ("L63", "rk4", 30), ("OU", "rk4", 75),
+                                            ("DW", "euler", 40), ("OU", "heun", 18)])
+def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
+    """Batches above 8192 problems run the staged forward sweep (small_dim.cu: blocks of time indices
+    through shared memory).  Its arithmetic is the per-thread kernel's, so a problem's result must be
+    bitwise the same in a 8 500-problem batch (staged; ragged last warp, ragged last block) and in a
+    small batch (register-prefetch kernel); sampled rows are also held to the oracle."""
+    from vgpa_b200.engine import BatchEvaluator
+    D = 3 if model == "L63" else 1
+    rng = np.random.default_rng(23)
+    M = 5
+    obs_t = np.linspace(0, N, M + 2, dtype=int)[1:-1]
+    theta = [10.0, 28.0, 2.6667] if model == "L63" else ([2.0] if model == "OU" else [1.0])
+    sig = np.full(D, 10.0 if model == "L63" else 0.8)
+    R = np.full(D, 2.0 if model == "L63" else 0.04)
+    B = 8500
+    obs_y = rng.standard_normal((B, M, D)) * (3.0 if model == "L63" else 0.5)
+    m0 = rng.standard_normal((B, D))
+    s0 = 0.25 * np.eye(D)
+    a_diag = 0.5 * sig / 0.25
+    x1 = np.concatenate([np.tile(np.diag(a_diag).ravel(), N), np.zeros(N * D)])
+    X = x1[None, :] + 0.05 * rng.standard_normal((B, x1.size))
+    with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y, m0, s0, np.zeros(B), B=B) as ev:
+        F, G = ev.eval(X)
+    rows = np.concatenate([np.arange(0, 40), np.arange(B - 40, B)])        # first warps and the ragged last one
+    with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows], m0[rows], s0,
+                        np.zeros(rows.size), B=rows.size) as ev:
+        Fs, Gs = ev.eval(X[rows])
+    assert np.array_equal(F[rows], Fs) and np.array_equal(G[rows], Gs)
+    for r in (0, 31, 4242, B - 1):
+        prob = Problem(model=model, method=method, D=D, N=N, dt=0.01, theta=theta, sigma=sig, R=R, obs_t=obs_t,
+                       obs_y=obs_y[r], m0=m0[r], s0=s0, E0=0.0)
+        Fo, Go = oracle.eval(prob, X[r])
+        assert abs(F[r] - Fo) <= TOL * abs(Fo)
+        assert rel_err(G[r], Go) < TOL
