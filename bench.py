@@ -266,7 +266,11 @@ def run_b200(args):
         traffic = None
         tpath = ROOT / "profiles" / "traffic_r01.json"
         if tpath.exists():
+            # the capture is of one 888-problem launch; `achieved` is per AVERAGE launch of the timed region
+            # (4096 = 4 x 888 + 544 problems per step), so the measured bytes are scaled to the same units
             traffic = json.loads(tpath.read_text()).get(dom)
+            if traffic is not None:
+                traffic = float(traffic) * units_per_launch / (888.0 * N_GRID)
         roofline = {"kernel": {"fwd": "l96_fwd_kernel", "energy": "l96_energy_kernel", "bwd": "l96_bwd_kernel"}[dom],
                     "bound": "tensor", "achieved": tflops, "peak": FP64_DMMA_TFLOPS, "unit": "TFLOP/s",
                     "frac": tflops / FP64_DMMA_TFLOPS, "traffic": traffic,
