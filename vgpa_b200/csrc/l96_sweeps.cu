@@ -222,7 +222,10 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
             else if (kind == K_CUR)   mma_rowa<0>(Ac, An, X, vX, irow, g, q, acc, yv);
             else if (kind == K_NEXT)  mma_rowa<0>(An, An, X, vX, irow, g, q, acc, yv);
             else                      mma_rowa<1>(Ac, An, X, vX, irow, g, q, acc, yv);
-            row_to_smem(sm.Tb, irow, q, acc);
+            // RK2's inner covariance stage multiplies S by itself: with S exactly symmetric the product is
+            // too, bit for bit (entry (j,i) is the same products accumulated in the same order), so its
+            // transpose is the accumulator itself: no exchange and no barrier before the epilogue
+            if (!self) row_to_smem(sm.Tb, irow, q, acc);
             {   // mean stage for row irow: k = -Aop v + bop
                 const double bv = kind == K_CUR ? bc : (kind == K_NEXT ? bn : 0.5 * (bc + bn));
                 const double ks = -yv + bv;
@@ -230,7 +233,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
                 if (wt != 0.0) kv = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * ks : kv + wt * ks;
                 if (sidx < NS - 1 && q == 0) sm.vt[sidx & 1][irow] = sm.mv[irow] + (next_coef(METHOD, sidx) * dt) * ks;
             }
-            __syncthreads();  // T complete / next mean operand visible
+            if (!self) __syncthreads();  // T complete
             {
                 const int i = irow;
 #pragma unroll
@@ -241,7 +244,8 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int j = j0 + e;
-                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + sm.Tb[sm_idx(j, i)]);
+                        const double pt = self ? acc[J][e] : sm.Tb[sm_idx(j, i)];
+                        const double kk = (i == j ? sm.sig[i] : 0.0) - (acc[J][e] + pt);
                         const double wt = ksum_w(METHOD, sidx);
                         if (wt != 0.0) ksum[J][e] = (sidx == 0 || (METHOD == ODE_RK2)) ? wt * kk : ksum[J][e] + wt * kk;
                         const double sold = e == 0 ? sv.x : sv.y;
