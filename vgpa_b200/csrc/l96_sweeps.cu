@@ -506,6 +506,10 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             }
         }
         if (t == 0) break;
+        // lam[t] (written at the end of the previous step, each warp its own rows) must be visible to every
+        // warp before the first mat-vec; the gradient above only reads a warp's own rows of it, so the
+        // barrier sits here and lets warps run ahead into the gradient of the next index
+        __syncthreads();
         // ---- one backward step t -> t-1 ------------------------------------------
         bool next_ready = false;
         double ksum[5][2];
@@ -630,9 +634,9 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
             }
             __syncwarp();
             if (q == 0) sm.lam[i] = ln;
+            __syncwarp();   // the other lanes of row i read it in the gradient of index t-1
             gcv = gnv;
         }
-        __syncthreads();  // lam of index t-1 visible to every warp
     }
 }
 
