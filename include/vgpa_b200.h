@@ -213,6 +213,8 @@ int vgpa_collect_obs_device(int device, int D, int N, int M, int B, const int64_
 /* Pinned host memory for x / grad staging (cudaHostAlloc / cudaFreeHost). */
 void *vgpa_host_alloc(int64_t bytes);
 void vgpa_host_free(void *p);
+/* memcpy on up to `threads` host threads (filling a pinned staging buffer from pageable memory). */
+void vgpa_host_copy(void *dst, const void *src, int64_t bytes, int threads);
 
 /* Introspection for bench.py: kernels launched by the handle so far, the
  * chunk size (problems resident per pass) and the scratch bytes in use. */
