@@ -105,6 +105,13 @@ const char *vgpa_last_error(const vgpa_handle *h);
 int vgpa_eval(vgpa_handle *h, const double *x, int64_t x_stride, int want_grad,
               double *F, double *grad, int64_t grad_stride);
 
+/* Optional active set for the following vgpa_eval_device calls: d_active = B int32 flags in DEVICE
+ * memory (read when the kernels run), NULL = every problem.  Problems whose flag is 0 are skipped by
+ * every kernel: their F, gradient rows and status are left untouched and they cost no sweep time.
+ * This is what lets a batched optimiser (SCG runs per problem, optim_scg.py:75-285) stop paying for
+ * problems that have converged. */
+int vgpa_set_active(vgpa_handle *h, const int32_t *d_active);
+
 /*
  * Same evaluation with DEVICE buffers on `stream` (a cudaStream_t passed as
  * void*; NULL = default stream).  Asynchronous: returns after enqueueing.

@@ -133,3 +133,41 @@ def test_misaligned_device_buffers_are_rejected():
         F = torch.zeros(1, dtype=torch.float64, device="cuda")
         with pytest.raises(ValueError):
             ev.eval_device(buf.data_ptr() + 8, ev.n_x, F.data_ptr(), None, None, 0)
+
+
+@pytest.mark.parametrize("name", ["eval_L96_rk2", "eval_L63_heun", "eval_OU_rk4"])
+def test_active_set_skips_problems(name):
+    """vgpa_set_active: problems flagged 0 are skipped by every kernel (F and gradient rows untouched),
+    the others get bitwise the result of the unmasked evaluation; NULL restores the full batch."""
+    import torch
+    from conftest import golden_eval_files
+    from test_gpu_parity import evaluator_from_golden
+    g = np.load(str(next(p for p in golden_eval_files() if name in p)))
+    B = 7
+    rng = np.random.default_rng(11)
+    X = np.stack([g["x"] * (1.0 + 1e-3 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    who = np.array([1, 0, 1, 1, 0, 0, 1], dtype=np.int32)
+    with evaluator_from_golden(g, B=B) as ev:
+        n = ev.n_x
+        Xd = torch.from_numpy(X).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        F0 = torch.empty(B, dtype=torch.float64, device="cuda")
+        G0 = torch.empty((B, n), dtype=torch.float64, device="cuda")
+        ev.eval_device(Xd.data_ptr(), n, F0.data_ptr(), G0.data_ptr(), n, st)
+        ev.sync()
+        F1 = torch.full((B,), -7.0, dtype=torch.float64, device="cuda")
+        G1 = torch.full((B, n), -7.0, dtype=torch.float64, device="cuda")
+        act = torch.from_numpy(who).cuda()
+        ev.set_active(act.data_ptr())
+        ev.eval_device(Xd.data_ptr(), n, F1.data_ptr(), G1.data_ptr(), n, st)
+        ev.sync()
+        ev.set_active(None)
+        F2 = torch.empty(B, dtype=torch.float64, device="cuda")
+        G2 = torch.empty((B, n), dtype=torch.float64, device="cuda")
+        ev.eval_device(Xd.data_ptr(), n, F2.data_ptr(), G2.data_ptr(), n, st)
+        ev.sync()
+    on = who.astype(bool)
+    F0, G0, F1, G1, F2, G2 = (t.cpu().numpy() for t in (F0, G0, F1, G1, F2, G2))
+    assert np.array_equal(F1[on], F0[on]) and np.array_equal(G1[on], G0[on])
+    assert np.all(F1[~on] == -7.0) and np.all(G1[~on] == -7.0)
+    assert np.array_equal(F2, F0) and np.array_equal(G2, G0)

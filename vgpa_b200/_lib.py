@@ -66,6 +66,8 @@ def _load():
     lib.vgpa_initialization_host.argtypes = [H, C.c_double, _dp, C.c_int64]
     lib.vgpa_sync.restype = C.c_int
     lib.vgpa_sync.argtypes = [H]
+    lib.vgpa_set_active.restype = C.c_int
+    lib.vgpa_set_active.argtypes = [H, C.c_void_p]
     lib.vgpa_eval_full.restype = C.c_int
     lib.vgpa_eval_full.argtypes = [H, C.c_int64, _dp, C.POINTER(VgpaFullOut)]
     lib.vgpa_solve_fwd.restype = C.c_int

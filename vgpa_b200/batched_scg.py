@@ -50,13 +50,25 @@ class BatchedSCG:
         self.sc = torch.empty(3 * B, dtype=torch.float64, device=dev)       # reduction outputs
         self.coef = torch.empty(B, dtype=torch.float64, device=dev)         # per-problem scalars in
         self.mask = torch.empty(B, dtype=torch.int32, device=dev)
+        self.act = torch.ones(B, dtype=torch.int32, device=dev)              # active set of the evaluations
         self.stream = torch.cuda.current_stream(dev).cuda_stream
         self.B, self.n = B, n
 
-    def _eval(self, X, G):
-        """F (host, B) and grad (device) at the rows of X."""
-        self.ev.eval_device(X.data_ptr(), self.n, self.Fd.data_ptr(), G.data_ptr(), self.n, self.stream)
-        self.ev.sync()
+    def _eval(self, X, G, who=None):
+        """F (host, B) and grad (device) at the rows of X.  `who` (B booleans): the problems that need
+        this evaluation; the kernels skip the others (vgpa_set_active), whose F entries and gradient
+        rows keep their previous content -- every use below is masked by the same condition.  A batch
+        thus stops paying for problems that have converged."""
+        if who is not None and not who.all():
+            self.act.copy_(self.torch.from_numpy(np.ascontiguousarray(who.astype(np.int32))))
+            self.ev.set_active(self.act.data_ptr())
+        else:
+            self.ev.set_active(None)
+        try:
+            self.ev.eval_device(X.data_ptr(), self.n, self.Fd.data_ptr(), G.data_ptr(), self.n, self.stream)
+            self.ev.sync()
+        finally:
+            self.ev.set_active(None)
         return self.Fd.cpu().numpy()
 
     def _dot(self, x, y, z=None):
@@ -133,7 +145,7 @@ class BatchedSCG:
                     S &= ~tiny
                 sigma = np.where(S, self.SIGMA0 / np.sqrt(np.where(kappa > 0, kappa, 1.0)), 0.0)
                 self._axpy(sigma, self.Dd, self.X, self.XT)           # x_plus = x + sigma d
-                self._eval(self.XT, self.GT)                          # df(x_plus, eval_fun=True)
+                self._eval(self.XT, self.GT, S)                       # df(x_plus, eval_fun=True)
                 st["evaluations"] += 1
                 st["f_eval"][S] += 1
                 st["df_eval"][S] += 1
@@ -146,7 +158,7 @@ class BatchedSCG:
             beta = np.where(neg, beta - theta / np.where(kappa != 0, kappa, 1.0), beta)
             alpha = np.where(active, -(mu / np.where(delta != 0, delta, 1.0)), 0.0)
             self._axpy(alpha, self.Dd, self.X, self.XT)               # x_new = x + alpha d
-            f_new = self._eval(self.XT, self.GT).copy()               # f(x_new); its gradient is kept
+            f_new = self._eval(self.XT, self.GT, active).copy()       # f(x_new); its gradient is kept
             st["evaluations"] += 1
             st["f_eval"][active] += 1
             # comparison ratio  (optim_scg.py:192-204)

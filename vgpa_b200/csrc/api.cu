@@ -419,6 +419,13 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
     return VGPA_OK;
 }
 
+int vgpa_set_active(vgpa_handle* h, const int32_t* d_active)
+{
+    if (!h) return VGPA_EINVAL;
+    h->batch.active = d_active;
+    return VGPA_OK;
+}
+
 int vgpa_sync(vgpa_handle* h)
 {
     if (!h) return VGPA_EINVAL;

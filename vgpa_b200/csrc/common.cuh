@@ -22,6 +22,8 @@ struct Batch {
     const double* m0;     long long m0_stride;
     const double* s0;     long long s0_stride;
     const double* E0;     long long E0_stride;
+    const int* active;        // B flags or null: problems whose flag is 0 are skipped by every kernel
+                              // (their F, gradient and scratch rows are left untouched)
 };
 
 // Per-pass (chunk) scratch: trajectories of the marginal moments, the SDE-energy

@@ -374,6 +374,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     const int g = lane >> 2, q = lane & 3;
     const int N = b.N;
     const int lp = blockIdx.x / N, t = blockIdx.x - lp * N, p = p0 + lp;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const double* At = x + (long long)p * xs + (long long)t * D * D;
     const double* bt = x + (long long)p * xs + (long long)N * D * D + (long long)t * D;
     const double* mt = s.mt + ((long long)lp * N + t) * D;

@@ -165,6 +165,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     const int g = lane >> 2, q = lane & 3;
     const int irow = 8 * w + g;
     const int lp = blockIdx.x, p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const double* A = x + (long long)p * xs;
     const double* bo = A + (long long)N * D * D;
     double* mt = s.mt + (long long)lp * N * D;
@@ -374,6 +375,7 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     const int g = lane >> 2, q = lane & 3;
     const int irow = 8 * w + g;   // the matrix / vector row of this lane
     const int lp = blockIdx.x, p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const double* A = a.A + (long long)lp * a.xs;
     const double* bo = a.bo ? a.bo + (long long)lp * a.xs : nullptr;
     const double* mt = a.mt ? a.mt + (long long)lp * a.traj_v : nullptr;

@@ -187,6 +187,7 @@ small_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
     const int lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= count) return;
     const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;
     const bool pf = count <= PF_MAX_BATCH;
     const double* A = x + (long long)p * xs;
     const double* bo = A + (long long)N * DD;
@@ -321,8 +322,8 @@ small_fwd_staged_kernel(Batch b, Scratch s, const double* __restrict__ x, long l
     double* sM = sS + 32 * PS;
     const int lane = threadIdx.x, lp0 = blockIdx.x * 32;
     const int nprob = min(32, count - lp0);
-    const bool on = lane < nprob;
-    const int lp = lp0 + (on ? lane : 0), p = p0 + lp, N = b.N;
+    const bool on = lane < nprob && (b.active == nullptr || b.active[p0 + lp0 + lane] != 0);
+    const int lp = lp0 + (lane < nprob ? lane : 0), p = p0 + lp, N = b.N;
     const double* A0 = x + (long long)(p0 + lp0) * xs;      // problem 0 of this warp
     const double* b0 = A0 + (long long)N * DD;
     double* mt0 = s.mt + (long long)lp0 * N * D;
@@ -331,6 +332,7 @@ small_fwd_staged_kernel(Batch b, Scratch s, const double* __restrict__ x, long l
     ld_vec<D>(b.sigma + p * b.sigma_stride, sig);
     ld_vec<D>(b.m0 + p * b.m0_stride, m);
     ld_vec<DD>(b.s0 + p * b.s0_stride, S);
+    // (a skipped problem's scratch rows receive whatever its shared-memory row holds: nobody reads them)
     if (on) {
 #pragma unroll
         for (int i = 0; i < D; ++i) mt0[(long long)lane * N * D + i] = m[i];
@@ -515,6 +517,7 @@ small_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long 
     const int N = b.N;
     if (idx >= (long long)count * N) return;
     const int lp = (int)(idx / N), t = (int)(idx % N), p = p0 + lp;
+    if (b.active != nullptr && b.active[p] == 0) return;
     const double* A = x + (long long)p * xs + (long long)t * DD;
     const double* bo = x + (long long)p * xs + (long long)N * DD + (long long)t * D;
     const double* th = b.theta + p * b.theta_stride;
@@ -684,6 +687,7 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
     const int lp = blockIdx.x * blockDim.x + threadIdx.x;
     if (lp >= count) return;
     const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;
     const bool pf = count <= PF_MAX_BATCH;
     const bool dense = a.jm_dense != nullptr;
     const double* A = a.x + (long long)p * a.xs;
@@ -832,6 +836,7 @@ finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, E
 {
     __shared__ double sh[128];
     const int lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const int N = b.N, D = b.D, M = b.M, DD = D * D;
     // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)
     const double* f = s.esde_t + (long long)lp * N;

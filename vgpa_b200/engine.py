@@ -123,6 +123,11 @@ class BatchEvaluator:
     def sync(self):
         raise_for(lib.vgpa_sync(self._h), self._h)
 
+    def set_active(self, mask_ptr=None):
+        """Device pointer to B int32 flags (0 = skip the problem in the following eval_device calls:
+        its F and gradient row stay untouched), or None for every problem."""
+        raise_for(lib.vgpa_set_active(self._h, mask_ptr), self._h)
+
     def initialization(self, t0=0.0):
         """VarGP.initialization for every problem of the batch, computed on the GPU: (B, n_x) host array."""
         X = np.empty((self.B, self.n_x))
