@@ -230,21 +230,24 @@ int64_t vgpa_chunk_size(const vgpa_handle *h);
 int64_t vgpa_scratch_in_use(const vgpa_handle *h);
 /* Batched vector kernels for the device-resident SCG driver (vgpa_b200/batched_scg.py):
  * the optimiser's own arithmetic (optim_scg.py:137-274) over rows of (B, n) DEVICE arrays
- * with a common row stride; one CTA per problem, fixed-order reductions.
+ * with a common row stride; rows are cut into slices so that small batches fill the GPU, and
+ * reductions add the slice partials in a fixed order.  `active` (B int32 flags in device memory,
+ * or NULL): rows whose flag is 0 are skipped and their outputs left untouched.
  *   vgpa_bdot  : out[p] = x.y, out[B+p] = x.z (z may be NULL), out[2B+p] = x.x
  *   vgpa_baxpy : out = y + a[p] x
  *   vgpa_bdir  : mode[p] 0 keep | 1: d = gamma[p] d - g | 2: d = -g
  *   vgpa_bcopy : dst[p] = src[p] where mask[p] != 0
  *   vgpa_bstats: out[p] = max|x|, out[B+p] = sum|x|                                   */
 int vgpa_bdot(int B, int64_t n, const double *x, const double *y, const double *z, int64_t stride,
-              double *out3B, void *stream);
+              double *out3B, const int32_t *active, void *stream);
 int vgpa_baxpy(int B, int64_t n, const double *a, const double *x, const double *y, double *out,
-               int64_t stride, void *stream);
+               int64_t stride, const int32_t *active, void *stream);
 int vgpa_bdir(int B, int64_t n, const int32_t *mode, const double *gamma, double *d, const double *g,
               int64_t stride, void *stream);
 int vgpa_bcopy(int B, int64_t n, const int32_t *mask, const double *src, double *dst, int64_t stride,
                void *stream);
-int vgpa_bstats(int B, int64_t n, const double *x, int64_t stride, double *out2B, void *stream);
+int vgpa_bstats(int B, int64_t n, const double *x, int64_t stride, double *out2B, const int32_t *active,
+                void *stream);
 
 /* Per-kernel device timing for bench.py's roofline: when enabled, every kernel
  * launch of vgpa_eval / vgpa_eval_device is bracketed by CUDA events on the

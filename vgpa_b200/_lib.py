@@ -103,11 +103,11 @@ def _load():
     lib.vgpa_get_timing.restype = C.c_int
     lib.vgpa_get_timing.argtypes = [H, _dp, _ip]
     vp, i32p = C.c_void_p, C.c_void_p
-    for name, args in (("vgpa_bdot", [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, vp]),
-                       ("vgpa_baxpy", [C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int64, vp]),
+    for name, args in (("vgpa_bdot", [C.c_int, C.c_int64, vp, vp, vp, C.c_int64, vp, i32p, vp]),
+                       ("vgpa_baxpy", [C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int64, i32p, vp]),
                        ("vgpa_bdir", [C.c_int, C.c_int64, i32p, vp, vp, vp, C.c_int64, vp]),
                        ("vgpa_bcopy", [C.c_int, C.c_int64, i32p, vp, vp, C.c_int64, vp]),
-                       ("vgpa_bstats", [C.c_int, C.c_int64, vp, C.c_int64, vp, vp])):
+                       ("vgpa_bstats", [C.c_int, C.c_int64, vp, C.c_int64, vp, i32p, vp])):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = args

@@ -47,10 +47,12 @@ class BatchedSCG:
         z = lambda: torch.empty((B, n), dtype=torch.float64, device=dev)
         self.XT, self.Gn, self.Go, self.GT, self.Dd = z(), z(), z(), z(), z()
         self.Fd = torch.empty(B, dtype=torch.float64, device=dev)
-        self.sc = torch.empty(3 * B, dtype=torch.float64, device=dev)       # reduction outputs
+        self.sc = torch.zeros(3 * B, dtype=torch.float64, device=dev)       # reduction outputs
         self.coef = torch.empty(B, dtype=torch.float64, device=dev)         # per-problem scalars in
         self.mask = torch.empty(B, dtype=torch.int32, device=dev)
         self.act = torch.ones(B, dtype=torch.int32, device=dev)              # active set of the evaluations
+        self.actv = torch.ones(B, dtype=torch.int32, device=dev)             # ... of the vector kernels
+        self._actv_ptr = None                                                # None = every row
         self.stream = torch.cuda.current_stream(dev).cuda_stream
         self.B, self.n = B, n
 
@@ -71,16 +73,25 @@ class BatchedSCG:
             self.ev.set_active(None)
         return self.Fd.cpu().numpy()
 
+    def _rows(self, active):
+        """Rows the vector kernels below work on: the problems still being optimised (a superset is
+        harmless: every use of their results is masked on the host)."""
+        if active.all():
+            self._actv_ptr = None
+        else:
+            self.actv.copy_(self.torch.from_numpy(np.ascontiguousarray(active.astype(np.int32))))
+            self._actv_ptr = self.actv.data_ptr()
+
     def _dot(self, x, y, z=None):
         raise_for(lib.vgpa_bdot(self.B, self.n, x.data_ptr(), y.data_ptr(), z.data_ptr() if z is not None else None,
-                                self.n, self.sc.data_ptr(), self.stream))
+                                self.n, self.sc.data_ptr(), self._actv_ptr, self.stream))
         r = self.sc.cpu().numpy().reshape(3, self.B)
         return r[0].copy(), r[1].copy(), r[2].copy()
 
     def _axpy(self, a, x, y, out):
         self.coef.copy_(self.torch.from_numpy(np.ascontiguousarray(a)))
         raise_for(lib.vgpa_baxpy(self.B, self.n, self.coef.data_ptr(), x.data_ptr(), y.data_ptr(), out.data_ptr(),
-                                 self.n, self.stream))
+                                 self.n, self._actv_ptr, self.stream))
 
     def _copy_where(self, m, src, dst):
         self.mask.copy_(self.torch.from_numpy(np.ascontiguousarray(m.astype(np.int32))))
@@ -94,7 +105,7 @@ class BatchedSCG:
                                 self.Gn.data_ptr(), self.n, self.stream))
 
     def _maxabs_sumabs(self, x):
-        raise_for(lib.vgpa_bstats(self.B, self.n, x.data_ptr(), self.n, self.sc.data_ptr(), self.stream))
+        raise_for(lib.vgpa_bstats(self.B, self.n, x.data_ptr(), self.n, self.sc.data_ptr(), self._actv_ptr, self.stream))
         r = self.sc.cpu().numpy()[:2 * self.B].reshape(2, self.B)
         return r[0].copy(), r[1].copy()
 
@@ -126,6 +137,7 @@ class BatchedSCG:
         for j in range(nit):
             if not active.any():
                 break
+            self._rows(active)
             S = success & active
             if S.any():
                 # first / second directional derivatives along d  (optim_scg.py:137-170)
