@@ -932,6 +932,11 @@ int vgpa_make_trajectory(int device, int model, int N, int B, double dt, const d
                          const double* z, int64_t z_stride, double* path, int64_t path_stride)
 {
     if (int rc = check_traj_args(model, N, B, dt, theta, sigma, x_init, z, path, z_stride, path_stride)) return rc;
+    if ((theta_stride != 0 && theta_stride < traj_ntheta(model)) || (sigma_stride != 0 && sigma_stride < model_dim(model)) ||
+        (x_init && x_init_stride != 0 && x_init_stride < model_dim(model))) {
+        g_create_error = "theta_stride / sigma_stride / x_init_stride shorter than one entry (0 = shared)";
+        return VGPA_EINVAL;
+    }
     if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
     const int D = model_dim(model);
     const int64_t len = (int64_t)N * D;
@@ -993,6 +998,11 @@ int vgpa_collect_obs(int device, int D, int N, int M, int B, const int64_t* obs_
     if (!obs_t || !R || !path || !xi || !obs_y) { g_create_error = "NULL argument"; return VGPA_EINVAL; }
     if (int rc = check_obs_args(D, N, M, B, obs_t)) return rc;
     if (M == 0) return VGPA_OK;
+    if ((R_stride != 0 && R_stride < D) || (path_stride != 0 && path_stride < (int64_t)N * D) ||
+        (xi_stride != 0 && xi_stride < (int64_t)M * D) || (B > 1 && obs_y_stride < (int64_t)M * D)) {
+        g_create_error = "R_stride / path_stride / xi_stride / obs_y_stride shorter than one entry (0 = shared)";
+        return VGPA_EINVAL;
+    }
     if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return VGPA_ECUDA; }
     const int64_t plen = (int64_t)N * D, olen = (int64_t)M * D;
     DevBuf dt_, dR, dp, dx, dy;
