@@ -200,8 +200,13 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     for (int k = 0; k < N - 1; ++k) {
         // launches of at most one CTA per SM (a single SCG run) have nothing to hide the DRAM latency of
         // their only input stream behind: pull this warp's eight rows of A into L2, PF_STEPS indices ahead
-        if (small_launch && lane == 0 && k + 1 + PF_STEPS < N)
-            bulk_prefetch_l2(A + (long long)(k + 1 + PF_STEPS) * D * D + (long long)(8 * w) * D, 8 * ROWB);
+        // Full waves look ahead ONE index only (7.6 MB in flight over 592 CTAs: nothing is evicted before
+        // use), which turns the register loads of A(k+2) a step later into L2 hits.
+        {
+            const int ahead = small_launch ? PF_STEPS : 1;
+            if (lane == 0 && k + 1 + ahead < N)
+                bulk_prefetch_l2(A + (long long)(k + 1 + ahead) * D * D + (long long)(8 * w) * D, 8 * ROWB);
+        }
         // A(k+1), b(k+1) for this step's later stages: loads stay in flight during stage 0
         {
             const double* an = arow + (long long)(k + 1) * D * D;
