@@ -79,3 +79,23 @@ def test_two_rank_gloo_matches_single_process(tmp_path, total):
         z = np.load(tmp_path / f"rank{r}.npz")
         assert np.array_equal(z["F"], F_ref)                       # bit for bit, on every rank
         assert np.array_equal(z["G"], G_ref[int(z["lo"]):int(z["hi"])])
+
+
+def test_shard_bounds_partition_property():
+    """Blocks are contiguous, ordered, cover [0, total) exactly once and differ in size by at most one."""
+    from hypothesis import given, settings, strategies as stg
+    from vgpa_b200.ensemble import shard_bounds
+
+    @settings(max_examples=200, deadline=None)
+    @given(total=stg.integers(0, 100000), world=stg.integers(1, 64))
+    def check(total, world):
+        blocks = [shard_bounds(total, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == total
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+        sizes = [hi - lo for lo, hi in blocks]
+        assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+        assert sizes == sorted(sizes, reverse=True)
+
+    check()
+    with pytest.raises(ValueError):
+        shard_bounds(10, 4, 4)
