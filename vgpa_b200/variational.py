@@ -57,6 +57,12 @@ class _GradientPool:
             else:                                         # still in use outside: never free under it
                 _STILL_REFERENCED.append((arr, ptr))
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def _diag(a, what):
     a = np.asarray(a, dtype=float)
