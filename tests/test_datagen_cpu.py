@@ -54,3 +54,14 @@ def test_host_mirror_reproduces_reference_stream(model):
     obs_t, obs_y, _ = proc.collect_obs(density, float(g["R"][0]) if D == 1 else g["R"])
     assert np.array_equal(np.asarray(obs_t), g["obs_t"])
     assert np.array_equal(obs_y, g["obs_y"])
+
+
+@pytest.mark.parametrize("model", ["L63", "L96"])
+def test_oracle_path_continues_from_a_given_state(oracle, model):
+    """x_init for the n-D models (no burn-in): a path restarted from its own state at index k with the
+    remaining draws is the tail of the original path, bit for bit."""
+    g = np.load(GOLDEN / f"datagen_{model}.npz")
+    N, k = int(g["N"]), 37
+    tail = oracle.make_trajectory(model, N - k, float(g["dt"]), theta_of(g), g["sigma"],
+                                  np.ascontiguousarray(g["z"][:, k:]), g["path"][k])
+    assert np.array_equal(tail, g["path"][k:])

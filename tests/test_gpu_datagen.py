@@ -106,3 +106,19 @@ def test_argument_errors():
         make_trajectories("L63", 10, -0.01, [10.0, 28.0, 2.7], [1.0] * 3, np.zeros((1, 3, 10)))
     with pytest.raises(ValueError):
         make_trajectories("XX", 10, 0.01, [1.0], [0.8], np.zeros((1, 10)), [0.0])
+
+
+@pytest.mark.parametrize("model", ["L63", "L96"])
+def test_path_continues_from_a_given_state(model):
+    """x_init for the n-D models (no burn-in), per path: restarted from the states at two different
+    indices with the remaining draws, the GPU gives the tails of the reference's path bit for bit."""
+    from vgpa_b200.engine import make_trajectories
+    g = np.load(GOLDEN / f"datagen_{model}.npz")
+    N, D = int(g["N"]), int(g["D"])
+    k1, k2 = 37, 90
+    n = N - k2
+    Z = np.stack([g["z"][:, k1:k1 + n], g["z"][:, k2:k2 + n]])
+    X0 = np.stack([g["path"][k1], g["path"][k2]])
+    tails = make_trajectories(model, n, float(g["dt"]), theta_of(g), g["sigma"], Z, X0)
+    assert np.array_equal(tails[0], g["path"][k1:k1 + n])
+    assert np.array_equal(tails[1], g["path"][k2:k2 + n])
