@@ -222,6 +222,10 @@ void *vgpa_host_alloc(int64_t bytes);
 void vgpa_host_free(void *p);
 /* memcpy on up to `threads` host threads (filling a pinned staging buffer from pageable memory). */
 void vgpa_host_copy(void *dst, const void *src, int64_t bytes, int threads);
+/* 1 when the two host ranges hold the same bytes (memcmp on up to `threads` host threads), else 0:
+ * the "is this the x of the last evaluation" test of VarGP.free_energy / gradient, whose reference
+ * counterpart recomputes unconditionally (variational.py:141-226). */
+int vgpa_host_equal(const void *a, const void *b, int64_t bytes, int threads);
 
 /* Introspection for bench.py: kernels launched by the handle so far, the
  * chunk size (problems resident per pass) and the scratch bytes in use. */

@@ -10,6 +10,7 @@ Run (authoring container only):
     python tests/golden/make_golden.py            # per-evaluation fixtures
     python tests/golden/make_golden.py --scg      # + SCG convergence traces
     python tests/golden/make_golden.py --l96-full # + L96 N=1001 known answers
+    python tests/golden/make_golden.py --no-eval --l96-mid   # L96 N=101, M=8: all intermediates
     python tests/golden/make_golden.py --no-eval --scg-full   # full SCG runs at the BASELINE shapes
 
 What is recorded per case (all float64, reference layouts):
@@ -179,6 +180,38 @@ def make_eval(ref):
                   f"|g|={np.linalg.norm(out['grad']):.6g} ({el:.2f}s)")
 
 
+def make_l96_mid(ref):
+    """L96 at tf = 1.0 (N = 101 grid points, M = 8 observations), RK2 and RK4: the multi-observation
+    jump logic of the backward sweep and the sn_diag quirk pinned at the INTERMEDIATE level
+    (lamt, psit, ...) for D = 40, which the tf = 0.2 fixtures (M = 1) cannot do.  The (N, D, D) arrays
+    are stored at a subset of time indices (every observation index, its neighbours, both ends and
+    every 8th index) to keep the fixture small; F, the gradient and the (N, D) arrays are complete."""
+    for method in ("rk2", "rk4"):
+        params = config("L96", method, 1.0)
+        sim, vgpa = build(ref, params)
+        x0 = vgpa.initialization()
+        x = perturb(x0, vgpa.dim_d, vgpa.dim_n, np.random.default_rng([SEED, 13]))
+        t0 = time.perf_counter()
+        out = evaluate(vgpa, x)
+        el = time.perf_counter() - t0
+        N = vgpa.dim_n
+        obs_t = np.asarray(sim.m_data["obs_t"], dtype=np.int64)
+        keep = set(range(0, N, 8)) | {0, 1, N - 2, N - 1}
+        for t in obs_t:
+            keep |= {int(t) - 1, int(t), int(t) + 1}
+        t_idx = np.array(sorted(k for k in keep if 0 <= k < N), dtype=np.int64)
+        rec = inputs_of(sim, vgpa, params, x)
+        for k, v in out.items():
+            rec[k] = v[t_idx] if (isinstance(v, np.ndarray) and v.ndim == 3) else v
+        rec["t_idx"] = t_idx
+        if method != "rk2":      # the evaluation point does not depend on the solver: stored once, in mid_L96_rk2.npz
+            assert np.array_equal(x, np.load(HERE / "mid_L96_rk2.npz")["x"])
+            del rec["x"]
+        name = HERE / f"mid_L96_{method}.npz"
+        np.savez_compressed(name, **rec)
+        print(f"{name.name}: N={N} M={obs_t.size} F={out['F']:.12g} kept {t_idx.size} of {N} indices ({el:.2f}s)")
+
+
 def make_scg(ref, which):
     """SCG convergence traces with the reference's own optimiser."""
     jobs = {"DW": (config("DW", "euler"), 500), "OU": (config("OU", "rk4"), 500),
@@ -287,6 +320,7 @@ if __name__ == "__main__":
     ap.add_argument("--l96-full", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--rosenbrock", action="store_true")
+    ap.add_argument("--l96-mid", action="store_true", help="L96 N=101, M=8 with all intermediates (RK2, RK4)")
     ap.add_argument("--scg-full", nargs="*", default=None,
                     help="full SCG runs at the BASELINE shapes (default: L63 L96; ~20 min of CPU)")
     a = ap.parse_args()
@@ -299,6 +333,8 @@ if __name__ == "__main__":
         make_l96_full(ref)
     if a.rosenbrock:
         make_scg_rosenbrock(ref)
+    if a.l96_mid:
+        make_l96_mid(ref)
     if a.scg_full is not None:
         make_scg_full(ref, a.scg_full or ["L63", "L96"])
     print(json.dumps({"numpy": np.__version__}))

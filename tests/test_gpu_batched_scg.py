@@ -53,3 +53,31 @@ def test_batched_scg_follows_single_problem_scg(name, max_it):
         assert abs(fx[p] - f1) <= 1e-6 * max(abs(f1), 1.0), p
         assert np.abs(Xh[p] - x1).max() <= 1e-5 * max(np.abs(x1).max(), 1.0), p
         assert np.allclose(st["beta"][:n, p], scg.stats["beta"][:n])
+
+
+@pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
+def test_batched_scg_matches_reference_scg_trace(model):
+    """Pinned to the REFERENCE directly: the problems of tests/golden/scg_<model>.npz (inputs and
+    the fx / beta traces recorded by the unmodified reference's own SCG + VarGP,
+    src/numerics/optim_scg.py:75-285), optimised on the device as a batch of three copies -- every
+    row must follow the reference trace within 1e-6 on the common prefix (BASELINE.json)."""
+    from conftest import GOLDEN
+    from test_gpu_parity import evaluator_from_golden
+    from vgpa_b200.batched_scg import BatchedSCG
+    g = np.load(GOLDEN / f"scg_{model}.npz")
+    B = 3
+    opts = {"max_it": int(g["max_it"]), "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False}
+    with evaluator_from_golden(g, B=B) as ev:
+        opt = BatchedSCG(ev, opts)
+        X, fx = opt(np.stack([g["x"]] * B))
+        st = opt.stats
+    n_ref = int(g["n_it"])
+    for p in range(B):
+        n_new = int(st["MaxIt"][p])
+        n = min(n_ref, n_new)
+        assert abs(n_ref - n_new) <= max(2, n_ref // 50), (p, n_ref, n_new)
+        ref, new = g["trace_fx"][:n], st["fx"][:n, p]
+        assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6, p
+        assert abs(fx[p] - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0), p
+        nb = min(n, 10)      # beta is a ratio of differences of nearly equal numbers: compare early iterations only
+        assert np.allclose(st["beta"][:nb, p], g["trace_beta"][:nb], rtol=1e-4), p

@@ -14,7 +14,7 @@ Also configs[2] at full size (L63, N=2002, RK2) and configs[1] (OU, N=1001, RK4)
 import numpy as np
 import pytest
 
-from conftest import golden_eval_files, rel_err
+from conftest import golden_eval_files, grad_err, rel_err
 from oracle import Problem
 from test_gpu_parity import evaluator_from_golden
 
@@ -56,7 +56,7 @@ def test_l96_ensemble_rows_match_oracle_at_full_size(oracle, l96_family):
                        m0=kw["m0"][r], s0=fam["s0"], E0=float(kw["E0"][r]), dt_model=fam["dt_model"])
         Fo, Go = oracle.eval(prob, X[r])
         assert abs(F[r] - Fo) <= TOL * abs(Fo), (p, F[r], Fo)
-        assert rel_err(G[r], Go) < TOL, p
+        assert grad_err(G[r], Go, prob.N, prob.D) < TOL, p
 
 
 def test_l96_batch_position_independence_bitwise(l96_family):
@@ -134,7 +134,7 @@ def test_small_models_at_full_size_match_oracle(oracle, model, method, N):
                        obs_y=obs_y[r], m0=m0[r], s0=s0, E0=0.0)
         Fo, Go = oracle.eval(prob, X[r])
         assert abs(F[r] - Fo) <= TOL * abs(Fo)
-        assert rel_err(G[r], Go) < TOL
+        assert grad_err(G[r], Go, prob.N, prob.D) < TOL
 
 
 @pytest.mark.parametrize("model,method,N", [("L63", "rk2", 61), ("L63", "rk4", 30), ("OU", "rk4", 75),
@@ -171,4 +171,4 @@ def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
                        obs_y=obs_y[r], m0=m0[r], s0=s0, E0=0.0)
         Fo, Go = oracle.eval(prob, X[r])
         assert abs(F[r] - Fo) <= TOL * abs(Fo)
-        assert rel_err(G[r], Go) < TOL
+        assert grad_err(G[r], Go, prob.N, prob.D) < TOL

@@ -6,7 +6,7 @@ device-resident ensemble variant against the host one.  Relative 1e-9 like the r
 import numpy as np
 import pytest
 
-from conftest import golden_eval_files, rel_err
+from conftest import golden_eval_files, grad_err, rel_err
 from test_gpu_parity import evaluator_from_golden
 from oracle import Problem
 
@@ -19,8 +19,9 @@ def test_initialization_matches_reference(oracle, path):
     g = np.load(path)
     with evaluator_from_golden(g) as ev:
         x0 = ev.initialization(0.0)[0]
-    assert rel_err(x0, g["x0"]) < TOL
-    assert rel_err(x0, oracle.initialization(Problem.from_golden(g), 0.0)) < TOL
+    N, D = int(g["N"]), int(g["D"])
+    assert grad_err(x0, g["x0"], N, D) < TOL
+    assert grad_err(x0, oracle.initialization(Problem.from_golden(g), 0.0), N, D) < TOL
 
 
 def test_batched_device_initialization_rows():

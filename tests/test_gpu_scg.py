@@ -140,17 +140,29 @@ def test_gradient_arrays_are_owned_by_the_caller():
     assert again is not held[3] and np.array_equal(again, copies[3])
     # dropping references lets buffers be reused: the pool stays small over many evaluations
     del held, again, g
-    n_buffers = len(vgpa._pin[1]._arrs)
+    import gc
+    gc.collect()
+    n_buffers = vgpa._pin[1]._allocated
     for k in range(24):
         x = xs[k % 6] * (1.0 + 1e-6 * k)
         vgpa.free_energy(x)
         last = vgpa.gradient(x)
-    assert len(vgpa._pin[1]._arrs) == n_buffers
+    assert vgpa._pin[1]._allocated == n_buffers and vgpa._pin[1].outstanding <= 2
     # more gradients alive than the pool holds: still correct (copies out of a private buffer)
     many = [vgpa.gradient(x * (1.0 + 1e-5 * k)) for k in range(12)]
     ref = vgpa.gradient(x * (1.0 + 1e-5 * 11))
     assert np.array_equal(many[11], ref) and len({id(m) for m in many}) == 12
     # closing the object must not pull the memory from under arrays the caller still holds
     keep = last.copy()
+    pool = vgpa._pin[1]
     vgpa.close()
     assert np.array_equal(last, keep) and np.array_equal(many[0], many[0].copy())
+    # ... and what the caller still holds frees itself when dropped (nothing is parked forever)
+    held_after_close = pool.outstanding
+    assert held_after_close >= 1
+    view = last[::2]
+    del last
+    assert pool.outstanding == held_after_close        # a view keeps its buffer alive
+    del view, many
+    gc.collect()
+    assert pool._closed and pool._free == []

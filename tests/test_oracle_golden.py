@@ -6,7 +6,7 @@ unmodified reference, must be reproduced to 1e-11 (observed: <= 4e-13).
 import numpy as np
 import pytest
 
-from conftest import golden_eval_files, rel_err
+from conftest import golden_eval_files, grad_err, key_err, rel_err
 from oracle import Problem
 
 KEYS = ("F", "E0", "Esde", "Eobs", "grad", "mt", "st", "lamt", "psit", "Efx", "Edf",
@@ -20,7 +20,7 @@ def test_oracle_reproduces_reference(oracle, path):
     prob = Problem.from_golden(g)
     out = oracle.eval(prob, g["x"], full=True)
     for k in KEYS:
-        assert rel_err(out[k], g[k]) < TOL, k
+        assert key_err(k, out[k], g[k], prob.N, prob.D) < TOL, k
 
 
 @pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
@@ -81,4 +81,41 @@ def test_oracle_initialization_reproduces_reference(oracle, path):
     g = np.load(path)
     prob = Problem.from_golden(g)
     x0 = oracle.initialization(prob, 0.0)
-    assert rel_err(x0, g["x0"]) < TOL
+    assert grad_err(x0, g["x0"], prob.N, prob.D) < TOL
+
+
+def load_mid(method):
+    """mid_L96_<method>.npz (L96, N = 101, M = 8 observations); the evaluation point is stored once."""
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden"
+    g = dict(np.load(gold / f"mid_L96_{method}.npz"))
+    if "x" not in g:
+        g["x"] = np.load(gold / "mid_L96_rk2.npz")["x"]
+    return g
+
+
+MID_3D = ("st", "psit", "Edf", "dEsde_ds")
+
+
+def mid_errors(out, g):
+    """Parity errors of every output of a mid_L96 fixture ((N, D, D) arrays at the stored indices)."""
+    N, D, t_idx = int(g["N"]), int(g["D"]), g["t_idx"]
+    errs = {}
+    for k in KEYS:
+        got = np.asarray(out[k])
+        if k in MID_3D:
+            got = got.reshape(N, D, D)[t_idx]
+        errs[k] = key_err(k, got, g[k], N, D)
+    return errs
+
+
+@pytest.mark.parametrize("method", ["rk2", "rk4"])
+def test_oracle_l96_eight_observations_all_intermediates(oracle, method):
+    """L96 with M = 8 observations: the jump logic of the backward sweep at every observation index and
+    the observation-ordinal quirk at the level of lamt / psit, not only through F."""
+    g = load_mid(method)
+    assert int(g["N"]) == 101 and g["obs_t"].size == 8
+    prob = Problem.from_golden(g)
+    out = oracle.eval(prob, g["x"], full=True)
+    bad = {k: e for k, e in mid_errors(out, g).items() if e >= TOL}
+    assert not bad, bad

@@ -92,6 +92,8 @@ def _load():
     lib.vgpa_host_free.argtypes = [C.c_void_p]
     lib.vgpa_host_copy.restype = None
     lib.vgpa_host_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.vgpa_host_equal.restype = C.c_int
+    lib.vgpa_host_equal.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     lib.vgpa_launch_count.restype = C.c_int64
     lib.vgpa_launch_count.argtypes = [H]
     lib.vgpa_chunk_size.restype = C.c_int64

@@ -1068,6 +1068,31 @@ void vgpa_host_copy(void* dst, const void* src, int64_t bytes, int threads)
     for (auto& t : pool) t.join();
 }
 
+int vgpa_host_equal(const void* a, const void* b, int64_t bytes, int threads)
+{
+    if (bytes <= 0) return 1;
+    if (!a || !b) return 0;
+    const int64_t min_part = 1 << 20;
+    const int n = (int)std::min<int64_t>(std::max(threads, 1), (bytes + min_part - 1) / min_part);
+    if (n <= 1) return std::memcmp(a, b, (size_t)bytes) == 0;
+    const int64_t part = ((bytes + n - 1) / n + 63) & ~int64_t(63);
+    std::vector<int> same(n, 1);
+    std::vector<std::thread> pool;
+    pool.reserve(n - 1);
+    for (int i = 1; i < n; ++i) {
+        const int64_t off = part * i;
+        if (off >= bytes) break;
+        const int64_t len = std::min(part, bytes - off);
+        int* out = &same[i];
+        pool.emplace_back([=]() { *out = std::memcmp((const char*)a + off, (const char*)b + off, (size_t)len) == 0; });
+    }
+    same[0] = std::memcmp(a, b, (size_t)std::min(part, bytes)) == 0;
+    for (auto& t : pool) t.join();
+    for (int v : same)
+        if (!v) return 0;
+    return 1;
+}
+
 int vgpa_set_timing(vgpa_handle* h, int enable)
 {
     if (!h) return VGPA_EINVAL;

@@ -31,6 +31,8 @@ def gather_free_energies(F_local, total, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     t = F_local if isinstance(F_local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(F_local))
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:
+        t = t.cuda()                      # NCCL moves device memory only (current CUDA device of this rank)
     sizes = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
     assert t.numel() == sizes[rank], (t.numel(), sizes[rank])
     if len(set(sizes)) == 1:
@@ -64,6 +66,29 @@ class ShardedEnsemble:
         self.evaluator = make_evaluator(self.lo, self.hi)
 
     def eval(self, X_local, want_grad=True):
-        """X_local: the rows [lo, hi) of the global X.  Returns (F_all (total,), grad_local)."""
+        """X_local: the rows [lo, hi) of the global X (host).  Returns (F_all (total,), grad_local)."""
         F_local, G_local = self.evaluator.eval(X_local, want_grad)
         return gather_free_energies(np.asarray(F_local), self.total, self.group), G_local
+
+    def eval_device(self, X, F, G=None, stream=0):
+        """Device-resident shard: X (rows, n_x), F (rows,), G (rows, n_x) or None are CUDA float64
+        torch tensors of this rank.  Asynchronous on `stream` (0 = the legacy default stream); call
+        `gather_device` for the one collective of the path."""
+        self.evaluator.eval_device(X.data_ptr(), X.stride(0) if X.dim() == 2 else 0, F.data_ptr(),
+                                   None if G is None else G.data_ptr(), None if G is None else G.stride(0), stream)
+
+    def gather_device(self, F):
+        """Wait for the shard's evaluation and gather F over the ranks (NCCL over NVLink): returns the
+        full (total,) CUDA tensor on every rank, or F itself without a process group."""
+        import torch
+        import torch.distributed as dist
+        self.evaluator.sync()
+        if not (dist.is_available() and dist.is_initialized()) or self.world == 1:
+            return F
+        sizes = [shard_bounds(self.total, r, self.world)[1] - shard_bounds(self.total, r, self.world)[0]
+                 for r in range(self.world)]
+        if len(set(sizes)) == 1:
+            out = torch.empty(self.total, dtype=F.dtype, device=F.device)
+            dist.all_gather_into_tensor(out, F.contiguous(), group=self.group)
+            return out
+        return torch.from_numpy(gather_free_energies(F, self.total, self.group)).to(F.device)

@@ -9,7 +9,7 @@ last x is cached so that `f(x)` followed by `df(x)` costs one evaluation instead
 of the reference's two.  There is no CPU path.
 """
 import ctypes as C
-import sys
+import weakref
 
 import numpy as np
 from scipy.interpolate import CubicSpline
@@ -17,45 +17,56 @@ from scipy.interpolate import CubicSpline
 from ._lib import PinnedArray, lib
 from .engine import BatchEvaluator
 
-_STILL_REFERENCED = []   # page-locked gradient buffers a caller still held when their VarGP was closed
-
-
 class _GradientPool:
     """Page-locked buffers for the gradient, handed to the caller WITHOUT a copy.
 
     `VarGP.gradient` must return an array the caller owns (optim_scg.py keeps the last two
     gradients alive).  Copying 13 MB out of a staging buffer and first-touching a fresh
     allocation costs about 2 ms per call at the L96 shape, so the device-to-host copy lands
-    directly in the array that is returned, and a buffer is reused only when no reference to it
-    is left outside the pool (the root array of each buffer is what the caller receives, so
-    every outside reference and every view shows in its reference count)."""
+    directly in the array that is returned.  Ownership is explicit: every array handed out is a
+    fresh ndarray object over one page-locked buffer with a `weakref.finalize` on it; views keep
+    that root array alive (their `.base`), so the finalizer runs exactly when the caller holds
+    nothing of the buffer any more, and only then does the buffer go back to the free list (or,
+    after `close()`, to `cudaFreeHost`)."""
 
     def __init__(self, n, max_buffers=8):
         self.n, self.max_buffers = int(n), int(max_buffers)
-        self._arrs, self._ptrs = [], []
+        self._free, self._allocated, self._closed = [], 0, False
 
     def take(self):
-        for i in range(len(self._arrs)):
-            if sys.getrefcount(self._arrs[i]) == 2:      # the list + getrefcount's argument
-                return self._arrs[i]
-        if len(self._arrs) >= self.max_buffers:
+        if self._free:
+            ptr = self._free.pop()
+        elif self._allocated < self.max_buffers:
+            ptr = lib.vgpa_host_alloc(max(self.n, 1) * 8)
+            if not ptr:
+                return None
+            self._allocated += 1
+        else:
             return None                                   # caller hoards gradients: fall back to copies
-        ptr = lib.vgpa_host_alloc(max(self.n, 1) * 8)
-        if not ptr:
-            return None
         buf = (C.c_double * max(self.n, 1)).from_address(ptr)
-        self._arrs.append(np.frombuffer(buf, dtype=np.float64, count=self.n))
-        self._ptrs.append(ptr)
-        return self._arrs[-1]
+        arr = np.frombuffer(buf, dtype=np.float64, count=self.n)
+        fin = weakref.finalize(arr, _GradientPool._release, weakref.ref(self), ptr)
+        fin.atexit = False                                # at interpreter exit the driver reclaims it
+        return arr
+
+    @staticmethod
+    def _release(pool_ref, ptr):
+        pool = pool_ref()
+        if pool is None or pool._closed:
+            lib.vgpa_host_free(ptr)
+        else:
+            pool._free.append(ptr)
+
+    @property
+    def outstanding(self):
+        """Buffers currently held by callers (or by the VarGP cache)."""
+        return self._allocated - len(self._free)
 
     def close(self):
-        while self._arrs:
-            arr, ptr = self._arrs.pop(), self._ptrs.pop()
-            if sys.getrefcount(arr) == 2:                 # the local name + getrefcount's argument
-                del arr
-                lib.vgpa_host_free(ptr)
-            else:                                         # still in use outside: never free under it
-                _STILL_REFERENCED.append((arr, ptr))
+        self._closed = True                               # buffers still held outside free themselves later
+        while self._free:
+            lib.vgpa_host_free(self._free.pop())
+            self._allocated -= 1
 
     def __del__(self):
         try:
@@ -71,6 +82,22 @@ def _diag(a, what):
             raise ValueError(f" VarGP: the CUDA path supports a diagonal {what} only.")
         return np.diagonal(a).copy()
     return np.atleast_1d(a)
+
+
+# the reference's dynamics classes carry no model key: recognise them by class name, so that the
+# reference's own objects can be handed to this VarGP unmodified
+_MODEL_KEY_BY_CLASS = {"DoubleWell": "DW", "OrnsteinUhlenbeck": "OU", "Lorenz63": "L63", "Lorenz96": "L96"}
+
+
+def _model_key(model):
+    key = getattr(model, "model_key", None)
+    if key is None:
+        for cls in type(model).__mro__:
+            if cls.__name__ in _MODEL_KEY_BY_CLASS:
+                return _MODEL_KEY_BY_CLASS[cls.__name__]
+        raise ValueError(f" VarGP: the CUDA path has no kernel for dynamics {type(model).__name__!r} "
+                         "(DoubleWell, OrnsteinUhlenbeck, Lorenz63, Lorenz96).")
+    return key
 
 
 class VarGP(object):
@@ -92,7 +119,6 @@ class VarGP(object):
         self._device = device
         self._ev_obj = None
         self._x_cached = None
-        self._x_obj = None
         self._x_probe = None
         self._f_cached = None
         self._g_cached = None
@@ -108,7 +134,7 @@ class VarGP(object):
             D = self.dim_d
             m0, s0 = self.output["m0"], self.output["s0"]
             self._ev_obj = BatchEvaluator(
-                model=self.model.model_key, method=self.fwd_ode.method, N=self.dim_n, dt=self.fwd_ode.dt,
+                model=_model_key(self.model), method=self.fwd_ode.method, N=self.dim_n, dt=self.fwd_ode.dt,
                 theta=np.atleast_1d(np.asarray(self.model.theta, dtype=float)),
                 sigma=_diag(self.model.sigma, "system noise"),
                 R=_diag(self.likelihood.noise, "observation noise"),
@@ -175,7 +201,6 @@ class VarGP(object):
         ev.eval(px, want_grad=True, F_out=F, G_out=g.reshape(1, -1))
         self.n_eval += 1
         self._x_cached = px
-        self._x_obj = x                         # the caller's array object (identity shortcut below)
         self._x_probe = px[::self._probe_step(px.size)].copy()
         self._f_cached = float(F[0])
         self._g_cached = g
@@ -186,10 +211,12 @@ class VarGP(object):
         return max(1, n // 2048)
 
     def _is_cached(self, x):
-        """Was the last evaluation at this x?  (The reference does not check at all: its gradient(x)
-        trusts the caller, variational.py:214-226.)  A strided probe of ~2000 entries rejects a new
-        point without touching the 13 MB array; the SCG's df(x) right after f(x) passes the same
-        array object, which is accepted on the probe alone; anything else gets the full comparison."""
+        """Was the last evaluation at this x?  (The reference does not check at all: it recomputes in
+        free_energy(x) and its gradient(x) trusts the caller, variational.py:141-226.)  A strided probe
+        of ~2000 entries rejects a new point without touching the 13 MB array; a point that passes the
+        probe is ALWAYS compared in full against the page-locked copy of the last x (multi-threaded
+        memcmp, ~0.4 ms at the L96 shape), so an array mutated in place between calls -- coordinate-wise
+        finite differences, sparse updates -- is never served from the cache."""
         if self._x_cached is None:
             return False
         xa = np.asarray(x).reshape(-1)
@@ -197,8 +224,8 @@ class VarGP(object):
             return False
         if not np.array_equal(xa[::self._probe_step(xa.size)], self._x_probe):
             return False
-        if x is self._x_obj:
-            return True
+        if xa.dtype == np.float64 and xa.flags.c_contiguous:
+            return bool(lib.vgpa_host_equal(xa.ctypes.data, self._x_cached.ctypes.data, xa.nbytes, 4))
         return np.array_equal(xa, self._x_cached)
 
     def free_energy(self, x):
