@@ -2,9 +2,14 @@
 // A(t), one launch of `problems` x N items; prints the kernel time and (VGPA_EN_PROF) the
 // average clock64 cycles CTA thread 0 spends in each phase.  Development aid.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I vgpa_b200/csrc -o tools/energy_prof tools/energy_prof.cu
+#ifndef VGPA_EN_NOPROF
 #define VGPA_EN_PROF
+#endif
 #include <cstdlib>
-#include "../vgpa_b200/csrc/l96_energy.cu"
+#ifndef VGPA_EN_SRC
+#define VGPA_EN_SRC "../vgpa_b200/csrc/l96_energy.cu"
+#endif
+#include VGPA_EN_SRC
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -49,19 +54,33 @@ int main(int argc, char** argv)
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 3; ++rep) {
         unsigned long long zero[32] = {0};
+#ifdef VGPA_EN_PROF
         CK(cudaMemcpyToSymbol(g_prof, zero, sizeof(zero)));
+#endif
         CK(cudaEventRecord(e0));
         launch_l96_energy(b, s, x, 0, 0, problems, ex, nullptr);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-        unsigned long long pr[32]; CK(cudaMemcpyFromSymbol(pr, g_prof, sizeof(pr)));
+        unsigned long long pr[32] = {0};
+#ifdef VGPA_EN_PROF
+        CK(cudaMemcpyFromSymbol(pr, g_prof, sizeof(pr)));
+#endif
         printf("{\"items\": %lld, \"ms\": %.3f, \"ns_per_item\": %.2f, \"phase_cycles\": [", items, ms, ms * 1e6 / items);
         double tot = 0;
-        for (int i = 0; i < 12; ++i) { printf("%s%.0f", i ? ", " : "", (double)pr[i] / items); tot += (double)pr[i] / items; }
+        for (int i = 0; i < 24; ++i) { printf("%s%.0f", i ? ", " : "", (double)pr[i] / items); if (i < 12) tot += (double)pr[i] / items; }
         std::vector<double> hes(8); CK(cudaMemcpy(hes.data(), es, 64, cudaMemcpyDeviceToHost));
         int hst; CK(cudaMemcpy(&hst, status, 4, cudaMemcpyDeviceToHost));
         printf("], \"total_cycles\": %.0f, \"esde0\": %.12g, \"status0\": %d}\n", tot, hes[0], hst);
+    }
+    if (argc > 3) {   // dump the outputs of the first problem (N items) for an A/B comparison of kernel versions
+        std::vector<double> o((size_t)N * (1 + Dd + Dd * Dd));
+        CK(cudaMemcpy(o.data(), es, (size_t)N * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(o.data() + N, dEm, (size_t)N * Dd * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(o.data() + N + (size_t)N * Dd, dEs, (size_t)N * Dd * Dd * 8, cudaMemcpyDeviceToHost));
+        FILE* f = fopen(argv[3], "wb");
+        fwrite(o.data(), 8, o.size(), f);
+        fclose(f);
     }
     return 0;
 }

@@ -30,12 +30,18 @@
 //          with the whole lower triangle in the registers of every lane (redundant, branch-free;
 //          lane c also solves column c of Tt_kk = Lt_kk^-1), announce it (named barrier, arrive),
 //          compute its own panel tile (k+1, k)
-//   followers (warps 1-3, one step behind): panels Lt_ik = C_ik Tt_kk^T D_k^-1 as DMMA tile
-//          products, trailing C_ij -= Lt_ik D_k Lt_jk^T, then in the shadow of the spine block
-//          row k of Vt and block column k of A Lt (in place over A; column 0 also gives A m)
-//   81 residual energies, one thread per sigma point;
+//   followers (warps 1-3, one step behind, STATIC work map): panels Lt_ik = C_ik Tt_kk^T D_k^-1 as
+//          DMMA tile products, trailing C_ij -= Lt_ik D_k Lt_jk^T, then in the shadow of the spine
+//          block row k of Vt (a warp per block column) and block column k of A Lt for the warp's
+//          own tile rows, whose A fragments stay in REGISTERS for the whole item (A m comes with
+//          their load; the product lands in place over A)
+//   81 residual energies: a thread serves both signs of a column, rows in three segments (123 threads);
 //   Vt^T diag(w / d) Vt on the lower tiles, mirrored on store; dE/dm from the same columns.
 // Shared-memory layout: common.cuh sm_idx (conflict-free for every access shape used here).
+// What bounds it (profiles/README.md, round 2): no single pipe -- issue slots ~56 %, L1 data pipe
+// ~65 %, FP64 pipe (DMMA + scalar, one pipe) ~53 % -- with dependent chains everywhere; the CODE SIZE
+// matters as much as the instruction count (the five CTAs of an SM sit in different phases: at 47 KB
+// of SASS the instruction cache hit rate fell to 87 % and two leaner variants ran 10 % slower).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -77,7 +83,7 @@ struct EnSmem {
     double dd[D];     // pivots d_j
     double rp[D];     // 1 / d_j
     double sdv[D];    // sqrt(c d_j): column scale of the sigma points
-    double var[K + 3];
+    double varp[3][K + 3];   // residual energies of the sigma points: partial sums over the three row segments
     int bad;
 };
 
@@ -88,8 +94,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-// named barriers (ids 1..): producer side arrives without blocking, consumer side waits
-// (ids and counts are immediates so that the compiler reserves exactly the barriers used)
+// named barriers (ids 1..): producer side arrives without blocking, consumer side waits -- the PTX
+// producer / consumer pattern (st.shared; bar.arrive | bar.sync; ld.shared), in which the barrier
+// itself orders the producer's earlier shared-memory stores before the consumer's loads.  (A
+// __threadfence_block() in front of the arrive compiles to MEMBAR.SC.CTA, ~150 cycles with stores in
+// flight, twice per block on the serial spine.)  Ids and counts are immediates so that the compiler
+// reserves exactly the barriers used.
 template <int ID>
 __device__ __forceinline__ void bar_sync()
 {
@@ -98,21 +108,19 @@ __device__ __forceinline__ void bar_sync()
 template <int ID>
 __device__ __forceinline__ void bar_arrive()
 {
-    // producer side of the PTX producer/consumer pattern (st.shared; bar.arrive | bar.sync; ld.shared);
-    // the block-scope fence makes the ordering of the preceding shared-memory stores explicit
-    __threadfence_block();
     asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(128) : "memory");
 }
 
-// reciprocal and reciprocal square root from the hardware seed (MUFU.RCP64H / RSQ64H, ~20 bits)
-// plus two Newton steps: full double precision without the long IEEE division / sqrt sequences
+// reciprocal from the hardware seed (MUFU.RCP64H, ~20 bits) and ONE cubically convergent step
+// r (1 + e + e^2), e = 1 - x r: three dependent FMAs instead of the four of two Newton steps (this
+// sits on the pivot-to-pivot chain of the factorisation); error ~ e^3 = 2^-60 before rounding.
+// Reciprocal square root: the hardware seed plus two Newton steps.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(fma(e, e, e), r, r);
 }
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
@@ -266,56 +274,93 @@ __device__ __forceinline__ void v_tile(EnSmem& sm, int I, int J, int g, int q)
     *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
 }
 
-// ---- tiles (i0, J) and (i0 + 1, J) of A Lt (PAIR: i0 + 1 < 5), in place over A: column J of Lt is
-//      final, columns > J of A intact.  The two tile rows share every B fragment.  Column 0 reads
-//      all of A, so cv = A m - b + theta comes with it (WITH_CV). ----------------------------
-template <bool PAIR, bool WITH_CV>
-__device__ __forceinline__ void al_tiles(EnSmem& sm, int i0, int J, double theta, int g, int q)
+
+// ---- block column J of A Lt for the tile rows of this warp, A fragments from REGISTERS (a0: tile
+//      row i0, a1: tile row i0 + 1 when `pair`), in place over A in shared memory: column J of Lt is
+//      final.  The tile rows share every B fragment; the two k-halves accumulate separately
+//      (half the dependent DMMA chain). ------------------------------------------------------
+__device__ __forceinline__ void al_col(EnSmem& sm, const double (&a0)[NB][2], const double (&a1)[NB][2], bool pair, int i0,
+                                       int J, int g, int q)
 {
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, y0 = 0.0, y1 = 0.0;
-    const double* aa = &sm.Ab[sm_idx(8 * i0 + g, q)];             // row 8 i0 + 8 + g has the same skew
+    double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, e[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const double* lb = &sm.Cb[8 * J + sm_boff(q, g)];             // B fragments of block column J
-#pragma unroll 1
-    for (int Kb = J; Kb < NB; ++Kb) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ko = 8 * Kb + 4 * h;
-            const double bf = lb[Kb * SM_R8 + h * SM_BH];
-            const double a0 = aa[ko];
-            dmma(c0, c1, a0, bf);
-            double a1 = 0.0;
-            if (PAIR) {
-                a1 = aa[SM_R8 + ko];
-                dmma(e0, e1, a1, bf);
-            }
-            if (WITH_CV) {
-                const double mk = sm.mv[ko + q];
-                y0 = fma(a0, mk, y0);
-                if (PAIR) y1 = fma(a1, mk, y1);
+    for (int Kb = 0; Kb < NB; ++Kb)
+        if (Kb >= J) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double bf = lb[Kb * SM_R8 + h * SM_BH];
+                dmma(c[h][0], c[h][1], a0[Kb][h], bf);
+                if (pair) dmma(e[h][0], e[h][1], a1[Kb][h], bf);
             }
         }
-    }
-    *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + g, 8 * J + 2 * q)]) = make_double2(c0, c1);
-    if (PAIR) *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + 8 + g, 8 * J + 2 * q)]) = make_double2(e0, e1);
-    if (WITH_CV) {
+    *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + g, 8 * J + 2 * q)]) = make_double2(c[0][0] + c[1][0], c[0][1] + c[1][1]);
+    if (pair)
+        *reinterpret_cast<double2*>(&sm.Ab[sm_idx(8 * i0 + 8 + g, 8 * J + 2 * q)]) =
+            make_double2(e[0][0] + e[1][0], e[0][1] + e[1][1]);
+}
+
+// ---- a follower warp (1..3) for the whole factorisation, one step behind the spine.  Per step kb:
+//        wait B1 (Tt_kk, Lt_kk, dd, rp of block kb are in place), my panel tile (kb + 1 + warp, kb),
+//        B2 (all panels of the column are in place), my trailing tiles of the step (static map
+//        `trail`: 8 bits per tile, i | j << 4, 4 tiles per step at most 3 used), B3 (arrive), and in
+//        the shadow of the spine what has just become final: tile (kb, warp - 1) of Vt and block
+//        column kb of A Lt for MY tile rows (A fragments in REGISTERS for the whole item: loaded
+//        once, the product lands in place over A; cv = A m - b + theta comes with the load).
+//      After the last diagonal block (CTA barrier): column 4 of A Lt and my tile of row 4 of Vt.
+__device__ __forceinline__ void follower(EnSmem& sm, int warp, double theta, int g, int q)
+{
+    // static work map (one code path for the three warps: the kernel's code size is what the instruction
+    // cache sees, profiles/README.md):           trailing tiles of steps 0 | 1 | 2        Vt column  A Lt rows
+    //   warp 1:  (2,1) (3,2) (4,3) | (3,2) (4,4) | (4,3)                                  0          4
+    //   warp 2:  (2,2) (3,3) (4,1) | (3,3) (4,2) | (4,4)                                  1          0, 1
+    //   warp 3:  (3,1) (4,2) (4,4) | (4,3)       | -                                      2          2, 3
+    const bool pair = warp != 1;
+    const int i0 = (warp == 1) ? 4 : (warp == 2 ? 0 : 2);
+    const unsigned trail0 = (warp == 1) ? 0x342312u : (warp == 2 ? 0x143322u : 0x442413u);
+    const unsigned trail1 = (warp == 1) ? 0x4423u : (warp == 2 ? 0x2433u : 0x34u);
+    const unsigned trail2 = (warp == 1) ? 0x34u : (warp == 2 ? 0x44u : 0u);
+    double a0[NB][2], a1[NB][2];
+    {
+        const double* aa = &sm.Ab[sm_idx(8 * i0 + g, q)];         // row 8 i0 + 8 + g has the same skew
+        const int o1 = pair ? SM_R8 : 0;
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+        for (int Kb = 0; Kb < NB; ++Kb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double mk = sm.mv[8 * Kb + 4 * h + q];
+                a0[Kb][h] = aa[8 * Kb + 4 * h];
+                a1[Kb][h] = aa[o1 + 8 * Kb + 4 * h];
+                y0 = fma(a0[Kb][h], mk, y0);
+                y1 = fma(a1[Kb][h], mk, y1);
+            }
         y0 += __shfl_xor_sync(0xffffffffu, y0, 1);
         y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
-        if (PAIR) {
-            y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
-            y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
-        }
+        y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+        y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
         if (q == 0) {
             sm.cv[8 * i0 + g] = (y0 - sm.bv[8 * i0 + g]) + theta;
-            if (PAIR) sm.cv[8 * i0 + 8 + g] = (y1 - sm.bv[8 * i0 + 8 + g]) + theta;
+            if (pair) sm.cv[8 * i0 + 8 + g] = (y1 - sm.bv[8 * i0 + 8 + g]) + theta;
         }
     }
-}
-// the three A Lt tasks of block column J: tile rows (0,1), (2,3), (4)
-template <bool WITH_CV>
-__device__ __forceinline__ void al_task(EnSmem& sm, int task, int J, double theta, int g, int q)
-{
-    if (task < 2) al_tiles<true, WITH_CV>(sm, 2 * task, J, theta, g, q);
-    else al_tiles<false, WITH_CV>(sm, 4, J, theta, g, q);
+#pragma unroll 1
+    for (int kb = 0; kb < NB; ++kb) {
+        if (kb < NB - 1) {
+            if (kb & 1) bar_sync<2>();                         // B1
+            else bar_sync<1>();
+            if (warp < NB - 1 - kb) panel_tile(sm, kb + 1 + warp, kb, g, q);
+            bar_sync<3>();                                     // B2
+#pragma unroll 1
+            for (unsigned w = (kb == 0) ? trail0 : (kb == 1 ? trail1 : (kb == 2 ? trail2 : 0u)); w != 0u; w >>= 8)
+                trail_tile(sm, (int)(w & 15u), (int)((w >> 4) & 15u), kb, g, q);
+            if (kb < NB - 2) bar_arrive<4>();                  // B3
+            if (warp - 1 < kb) v_tile(sm, kb, warp - 1, g, q);
+        } else {
+            __syncthreads();                                   // the last diagonal block is in place
+        }
+        al_col(sm, a0, a1, pair, i0, kb, g, q);
+    }
 }
 
 // ---- tile-row I of dEsde/dS = (c/2) Vt^T diag(dw) Vt (lower tiles J <= I), mirrored on store,
@@ -421,7 +466,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
                 const int r = tid - 2 * D;
                 bulk_prefetch_l2(s.st + nb * (D * D) + r * D, 64 * ((r >> 3) + 1));
             } else if (tid == 3 * D) {
-                const int lpn = (int)(nb / N), tn = (int)(nb - (long long)lpn * N);
+                const unsigned tq = (unsigned)(t + AHEAD) / (unsigned)N;      // 32-bit: no 64-bit division sequence
+                const int lpn = lp + (int)tq, tn = t + AHEAD - (int)tq * N;
                 bulk_prefetch_l2(x + (long long)(p0 + lpn) * xs + (long long)tn * D * D, D * ROWB);
             }
         }
@@ -473,6 +519,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     // column are in place), the trailing update of step kb (announced on B3, which warp 0 checks
     // just before it touches tiles of the next column), and then, in the shadow of the spine, what
     // has just become final: block row kb of Vt and block column kb of A Lt.
+    // (Rotating the roles with the CTA, so that the spines of the co-resident CTAs do not all sit on
+    // sub-partition 0, was measured: 3 % SLOWER -- the spines run best away from the tile work.)
     if (warp == 0) {
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) {
@@ -490,36 +538,15 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
                 __syncwarp();
             }
         }
+        PROF_MARK(1);
+        __syncthreads();
     } else {
-#pragma unroll 1
-        for (int kb = 0; kb < NB - 1; ++kb) {
-            if (kb & 1) bar_sync<2>();                         // B1
-            else bar_sync<1>();
-            if (warp < NB - 1 - kb) panel_tile(sm, kb + 1 + warp, kb, g, q);
-            bar_sync<3>();                                     // B2
-            int n = 3 - warp;           // round-robin over warps 1..3: a task is mine when n hits 3
-            for (int i = kb + 2; i < NB; ++i)
-                for (int j = kb + 1; j <= i; ++j)
-                    if (++n == 3) { n = 0; trail_tile(sm, i, j, kb, g, q); }
-            if (kb < NB - 2) bar_arrive<4>();                  // B3
-            for (int j = 0; j < kb; ++j)
-                if (++n == 3) { n = 0; v_tile(sm, kb, j, g, q); }
-            // A Lt, block column kb: three tasks (tile rows (0,1), (2,3), (4)); column 0 also gives cv
-            for (int task = 0; task < 3; ++task)
-                if (++n == 3) {
-                    n = 0;
-                    if (kb == 0) al_task<true>(sm, task, kb, theta, g, q);
-                    else al_task<false>(sm, task, kb, theta, g, q);
-                }
-        }
+        follower(sm, warp, theta, g, q);
     }
-    PROF_MARK(1);
-    __syncthreads();
     PROF_MARK(2);
-    // ---- what needed the last diagonal block: row 4 of Vt, column 4 of A Lt, the column scales ----
+    // ---- what needed the last diagonal block: row 4 of Vt (column 4 of A Lt: follower()), the column scales ----
     {
         v_tile(sm, 4, warp, g, q);
-        if (warp < 3) al_task<false>(sm, warp, 4, theta, g, q);
         if (tid < D) {
             const double cd = c * sm.dd[tid];
             sm.sdv[tid] = cd * fast_rsqrt(cd);
@@ -529,39 +556,75 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     __syncthreads();
     PROF_MARK(8);
 
-    // ---- residual energies of the 81 sigma points: ONE THREAD PER SIGMA POINT walks the 40
-    //      state entries with a sliding window (x[i-2], x[i-1], x[i], x[i+1]); lanes of a
-    //      warp read consecutive columns of Lt and A Lt (conflict-free), the per-entry
-    //      constants are warp-uniform broadcasts, and no cross-lane reduction is needed.
-    //      The upper triangle of the Lt buffer is true zeros, so no selects are needed ----
-    if (tid < K) {
-        const int k = tid;
-        const int kp = (k == 0) ? K - 1 : k - 1, kn = (k == K - 1) ? 0 : k + 1;
-        const int col = (k == 0) ? 0 : ((k <= D) ? k - 1 : k - 1 - D);
-        const int colp = (kp == 0) ? 0 : ((kp <= D) ? kp - 1 : kp - 1 - D);
-        const int coln = (kn == 0) ? 0 : ((kn <= D) ? kn - 1 : kn - 1 - D);
-        const double sg = (k == 0) ? 0.0 : ((k <= D) ? sm.sdv[col] : -sm.sdv[col]);     // +- sqrt(c d_col)
-        const double sgp = (kp == 0) ? 0.0 : ((kp <= D) ? sm.sdv[colp] : -sm.sdv[colp]);
-        const double sgn = (kn == 0) ? 0.0 : ((kn <= D) ? sm.sdv[coln] : -sm.sdv[coln]);
+    // ---- residual energies of the 81 sigma points.  One thread serves BOTH sigma points m +- s L[:, col]
+    //      of a column (they share every load: the column entries of Lt and A Lt, m, cv, 1 / sigma); the
+    //      centre point is a 41st "column" with s = 0.  The 40 state entries are cut into three segments
+    //      (rows 0..13, 14..26, 27..39), so 41 x 3 = 123 threads each walk at most 14 rows with a sliding
+    //      window (x[i-2], x[i-1], x[i], x[i+1]) per sign; the three partial sums of a sigma point are
+    //      added in a fixed order below.  (One thread per sigma point over all 40 rows: 81 threads, 40
+    //      dependent steps, 975 shared-memory wavefronts per item; this: 14 steps, ~600 wavefronts.)
+    //      The upper triangle of the Lt buffer is true zeros: no selects. ----
+    if (tid < 3 * (D + 1)) {
+        const int seg = tid / (D + 1), task = tid - seg * (D + 1);
+        const int i0 = (seg == 0) ? 0 : (seg == 1 ? 14 : 27), i1 = (seg == 0) ? 14 : (seg == 1 ? 27 : D);
+        const bool centre = task == D;
+        const int col = centre ? 0 : task;
+        const double sd = centre ? 0.0 : sm.sdv[col];                           // sqrt(c d_col)
         const double* Lc = sm.Cb + col;
         const double* ALc = sm.Ab + col;
-        // the flattened roll (lorenz_96.py:27-32) wraps into the neighbouring sigma points
-        double xm2 = fma(sgp, sm.Cb[sm_idx(D - 2, colp)], sm.mv[D - 2]);
-        double xm1 = fma(sgp, sm.Cb[sm_idx(D - 1, colp)], sm.mv[D - 1]);
-        double x0 = fma(sg, Lc[0], sm.mv[0]);
-        const double xwrap = fma(sgn, sm.Cb[coln], sm.mv[0]);
-        double var = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < D; ++i) {
-            const double xp1 = (i + 1 < D) ? fma(sg, Lc[sm_idx(i + 1, 0)], sm.mv[i + 1]) : xwrap;
-            const double fx = fma(xp1 - xm2, xm1, -x0);                 // lorenz_96.py:85-101 (theta is in cv)
-            const double r = fx + fma(sg, ALc[sm_idx(i, 0)], sm.cv[i]);
-            var = fma(sm.isg[i] * r, r, var);
-            xm2 = xm1;
-            xm1 = x0;
-            x0 = xp1;
+        // windows of the two signs at the first row of the segment
+        double pm2, pm1, p0, qm2, qm1, q0;      // p: m + sd L[:, col] (or the centre point), q: m - sd L[:, col]
+        {
+            // the flattened roll (lorenz_96.py:27-32) wraps rows -2, -1 of a sigma point into the PREVIOUS
+            // one: +col follows +(col-1) (+0 follows the centre), -col follows -(col-1) (-0 follows +39),
+            // the centre follows -39.  Inside a segment the "previous rows" are the thread's own column.
+            const int colp = (seg != 0) ? col : ((centre || col == 0) ? D - 1 : col - 1);
+            const double sp = (seg != 0) ? sd : sm.sdv[colp];
+            const double sgp_p = (seg != 0) ? sd : (centre ? -sp : (col == 0 ? 0.0 : sp));
+            const double sgp_q = (seg != 0) ? -sd : (col == 0 ? sp : -sp);
+            const int r2 = (seg != 0) ? i0 - 2 : D - 2, r1 = (seg != 0) ? i0 - 1 : D - 1;
+            const double l2 = sm.Cb[sm_idx(r2, colp)], l1 = sm.Cb[sm_idx(r1, colp)], l0 = Lc[sm_idx(i0, 0)];
+            pm2 = fma(sgp_p, l2, sm.mv[r2]);
+            pm1 = fma(sgp_p, l1, sm.mv[r1]);
+            qm2 = fma(sgp_q, l2, sm.mv[r2]);
+            qm1 = fma(sgp_q, l1, sm.mv[r1]);
+            p0 = fma(sd, l0, sm.mv[i0]);
+            q0 = fma(-sd, l0, sm.mv[i0]);
         }
-        sm.var[k] = var;
+        // row 40 wraps into row 0 of the NEXT sigma point: +col -> +(col+1) (+39 -> -0), -col -> -(col+1)
+        // (-39 -> the centre), the centre -> +0
+        double pwrap = 0.0, qwrap = 0.0;
+        if (seg == 2) {
+            const int coln = (centre || col == D - 1) ? 0 : col + 1;
+            const double sn = sm.sdv[coln], l0n = sm.Cb[coln];
+            const double sgn_p = centre ? sn : (col == D - 1 ? -sn : sn);
+            const double sgn_q = (col == D - 1) ? 0.0 : -sn;
+            pwrap = fma(sgn_p, l0n, sm.mv[0]);
+            qwrap = fma(sgn_q, l0n, sm.mv[0]);
+        }
+        double vp = 0.0, vq = 0.0;
+#pragma unroll 2
+        for (int i = i0; i < i1; ++i) {
+            double pp1 = pwrap, qp1 = qwrap;
+            if (i + 1 < D) {
+                const double l1 = Lc[sm_idx(i + 1, 0)], m1 = sm.mv[i + 1];
+                pp1 = fma(sd, l1, m1);
+                qp1 = fma(-sd, l1, m1);
+            }
+            const double al = sd * ALc[sm_idx(i, 0)], cvi = sm.cv[i], isg = sm.isg[i];
+            const double rp_ = fma(pp1 - pm2, pm1, -p0) + (cvi + al);           // lorenz_96.py:85-101 (theta is in cv)
+            const double rq_ = fma(qp1 - qm2, qm1, -q0) + (cvi - al);
+            vp = fma(isg * rp_, rp_, vp);
+            vq = fma(isg * rq_, rq_, vq);
+            pm2 = pm1; pm1 = p0; p0 = pp1;
+            qm2 = qm1; qm1 = q0; q0 = qp1;
+        }
+        if (centre) {
+            sm.varp[seg][0] = vp;
+        } else {
+            sm.varp[seg][1 + col] = vp;
+            sm.varp[seg][1 + D + col] = vq;
+        }
     }
     __syncthreads();
     PROF_MARK(9);
@@ -573,13 +636,15 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         // computes it and the 40 + 40 weights below and stores them (same values, same addresses),
         // so only a warp-level sync separates this from the tile products that read them.
         double e = 0.0;
-        for (int k = lane; k < K; k += 32) e += (k == 0 ? w0 : wi) * sm.var[k];
+        for (int k = lane; k < K; k += 32)
+            e += (k == 0 ? w0 : wi) * ((sm.varp[0][k] + sm.varp[1][k]) + sm.varp[2][k]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
         e *= 0.5;
         esde = e;
         for (int j = lane; j < D; j += 32) {
-            const double vp = sm.var[1 + j], vm = sm.var[1 + D + j];
+            const double vp = (sm.varp[0][1 + j] + sm.varp[1][1 + j]) + sm.varp[2][1 + j];
+            const double vm = (sm.varp[0][1 + D + j] + sm.varp[1][1 + D + j]) + sm.varp[2][1 + D + j];
             // V = diag(dd^-1/2) Vt: fold the scales into the weights
             sm.bv[j] = (wi * (vp - vm)) * fast_rsqrt(sm.dd[j]);                 // q_j / sqrt(d_j)
             sm.cv[j] = (0.5 * (wi * (vp + vm)) - e * (1.0 / c)) * sm.rp[j];     // d_j-weight / d_j
