@@ -57,13 +57,15 @@ def import_reference():
                 PriorKL0=PriorKL0, VarGP=VarGP, SCG=SCG, root=str(root))
 
 
-def reference_objects(ref, params):
+def reference_objects(ref, params, override=None):
     """Simulation.setup (simulation.py:92-176) and the constructor block of Simulation.run
-    (simulation.py:189-207) with the reference's own classes: everything VarGP's constructor takes."""
+    (simulation.py:189-207) with the reference's own classes: everything VarGP's constructor takes.
+    `override`: entries of Simulation.m_data replaced after setup (e.g. obs_y, m0 of an ensemble member)."""
     with contextlib.redirect_stdout(io.StringIO()):
         sim = ref["Simulation"](params.get("Output_Name", "ref"))
         sim.setup(params, None)
     md = sim.m_data
+    md.update(override or {})
     dt = md["time_window"]["dt"]
     fwd = ref["FwdOde"](dt, md["ode_solver"], md["single_dim"])
     bwd = ref["BwdOde"](dt, md["ode_solver"], md["single_dim"])

@@ -30,6 +30,12 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "L96" in d["config"]["workload"]
+    # what the arm times is said at the top level, and the unmodified Python reference is timed beside it
+    assert d["reference_kind"] == "port"
+    cal = d["cpu_baseline_reference"]
+    assert cal["kind"] == "reference"
+    if "unavailable" not in cal:          # baseline/_ref + numba present: the reference's known answer at x0
+        assert abs(cal["F_x0"] - 49769.73517670352) < 1e-6 and 0 < cal["value"] < d["value"]
     # the two arms must agree on what they measure
     src = (ROOT / "bench.py").read_text()
     assert src.count('"metric": METRIC') == 2 and src.count('"workload": WORKLOAD') == 2
