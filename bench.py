@@ -328,7 +328,8 @@ def secondary_configs(torch, local, hbm_peak):
         Dm = 1 if path.ndim == 1 else path.shape[1]
         Nn = path.shape[0]
         obs_t = np.asarray(md["obs_t"], dtype=np.int64)
-        R = np.full(Dm, float(md["obs_noise"]))
+        R = np.asarray(md["obs_noise"], dtype=float)
+        R = np.diagonal(R).copy() if R.ndim == 2 else np.full(Dm, float(R))
         obs_y = np.empty((Bn, obs_t.size, Dm))
         m0 = np.empty((Bn, Dm))
         for p_ in range(Bn):                      # per-problem observation noise and m0
@@ -365,7 +366,8 @@ def secondary_configs(torch, local, hbm_peak):
                      "evals_per_s": round(Bn / (ms * 1e-3), 1),
                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                                   "frac": round(gbs / hbm_peak, 4)},
-                     "l2": "working set %.0f MB (fits L2 for the small batches: stated, not flushed)" % (Bn * 2 * 8.0 * nx / 1e6)}
+                     "l2": ("working set (x + grad) %.0f MB: %s" % (Bn * 2 * 8.0 * nx / 1e6, "larger than the 126 MB L2"
+                            if Bn * 2 * 8.0 * nx > 126e6 else "fits the 126 MB L2 (not flushed between iterations: stated)"))}
         del X, G, F
 
     batch("OU_x1024_rk4_N1001", base("OU", "RK4", 10.0, 0.8, 0.04, 2, 2.0), 1024)
