@@ -112,6 +112,14 @@ int vgpa_eval(vgpa_handle *h, const double *x, int64_t x_stride, int want_grad,
  * problems that have converged. */
 int vgpa_set_active(vgpa_handle *h, const int32_t *d_active);
 
+/* Compacted launches for thinned-out ensembles (Lorenz-96, D = 40 only): `list` = n problem indices in
+ * HOST memory (copied), or NULL / n < 0 to switch the mode off.  The following vgpa_eval_device calls
+ * evaluate exactly the listed problems, chunked by list position, so that every pass still fills whole
+ * waves of the GPU when most problems of a batch have converged (an active-flag mask alone leaves the
+ * chunk of a few survivors under-occupied).  F and gradient rows are still addressed by problem index;
+ * the rows of unlisted problems are left untouched.  Host-buffer entry points ignore the list. */
+int vgpa_set_active_list(vgpa_handle *h, const int32_t *list, int32_t n);
+
 /*
  * Same evaluation with DEVICE buffers on `stream` (a cudaStream_t passed as
  * void*; NULL = default stream).  Asynchronous: returns after enqueueing.

@@ -81,3 +81,74 @@ def test_batched_scg_matches_reference_scg_trace(model):
         assert abs(fx[p] - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0), p
         nb = min(n, 10)      # beta is a ratio of differences of nearly equal numbers: compare early iterations only
         assert np.allclose(st["beta"][:nb, p], g["trace_beta"][:nb], rtol=1e-4), p
+
+
+def test_compacted_launch_equals_masked_launch_bitwise():
+    """vgpa_set_active_list (compacted launches of the D = 40 kernels, used by BatchedSCG once part of a
+    batch has converged): the listed problems get bit-identical F and gradients to a full evaluation, the
+    others are left untouched; the host entry points ignore the list."""
+    import torch
+    from test_gpu_parity import evaluator_from_golden
+    g = _load("eval_L96_rk2")
+    B = 7
+    rng = np.random.default_rng(5)
+    X = np.stack([g["x"] * (1.0 + 0.01 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    sigma = np.stack([g["sigma"] * (0.9 + 0.05 * i) for i in range(B)])
+    with evaluator_from_golden(g, B=B, sigma=sigma) as ev:
+        F_ref, G_ref = ev.eval(X)
+        Xd = torch.from_numpy(X).cuda()
+        Fd = torch.full((B,), -1.0, dtype=torch.float64, device="cuda")
+        Gd = torch.full_like(Xd, -2.0)
+        st = torch.cuda.current_stream().cuda_stream
+        pick = np.array([5, 1, 2])                     # any order, any subset
+        ev.set_active_list(pick)
+        ev.eval_device(Xd.data_ptr(), ev.n_x, Fd.data_ptr(), Gd.data_ptr(), ev.n_x, st)
+        ev.sync()
+        F, G = Fd.cpu().numpy(), Gd.cpu().numpy()
+        rest = np.setdiff1d(np.arange(B), pick)
+        assert np.array_equal(F[pick], F_ref[pick]) and np.array_equal(G[pick], G_ref[pick])
+        assert np.all(F[rest] == -1.0) and np.all(G[rest] == -2.0)
+        F2, G2 = ev.eval(X)                            # host buffers: every problem, list or not
+        assert np.array_equal(F2, F_ref) and np.array_equal(G2, G_ref)
+        ev.set_active_list(None)
+        ev.eval_device(Xd.data_ptr(), ev.n_x, Fd.data_ptr(), Gd.data_ptr(), ev.n_x, st)
+        ev.sync()
+        assert np.array_equal(Fd.cpu().numpy(), F_ref) and np.array_equal(Gd.cpu().numpy(), G_ref)
+    g1 = _load("eval_OU_rk4")
+    with evaluator_from_golden(g1, B=3) as ev1:
+        with pytest.raises(ValueError):
+            ev1.set_active_list([0, 2])                # compacted launches exist for Lorenz-96 only
+
+
+def test_sharded_batched_scg_single_gpu_sub_batches(tmp_path):
+    """ShardedBatchedSCG on one GPU: an ensemble optimised in resident sub-batches gives, problem by problem,
+    what one BatchedSCG over the whole ensemble gives; the ensemble file carries the reference's keys."""
+    from oracle import prior_kl0
+    from vgpa_b200.batched_scg import BatchedSCG, ShardedBatchedSCG
+    from vgpa_b200.engine import BatchEvaluator
+    from vgpa_b200.simulation import load
+    g = _load("eval_L63_heun")
+    D, N, B = int(g["D"]), int(g["N"]), 10
+    rng = np.random.default_rng([9, D])
+    obs_y = np.stack([g["obs_y"] + 0.05 * rng.standard_normal(g["obs_y"].shape) for _ in range(B)])
+    E0 = float(prior_kl0(g["m0"], g["s0"], g["mu0"], g["tau0"], False))
+    common = dict(model="L63", method="heun", N=N, dt=float(g["dt"]), theta=g["theta"], sigma=g["sigma"], R=g["R"],
+                  obs_t=g["obs_t"], m0=g["m0"], s0=g["s0"], E0=E0, dt_model=float(g["dt"]))
+    opts = {"max_it": 25, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False}
+    make = lambda lo, hi: BatchEvaluator(obs_y=obs_y[lo:hi], B=hi - lo, **common)
+    ens = ShardedBatchedSCG(B, make, opts, sub_batch=4)
+    res = ens.run(t0=0.0, keep=(0, 7))
+    with make(0, B) as ev:
+        X0 = ev.initialization(0.0)
+        opt = BatchedSCG(ev, opts)
+        X, fx = opt(X0)
+        Xh = X.cpu().numpy()
+    assert np.allclose(res["fx"], fx, rtol=1e-12) and np.array_equal(res["n_it"], opt.stats["MaxIt"])
+    assert np.allclose(res["kept"][7], Xh[7], rtol=1e-12, atol=1e-14)
+    assert res["sub_batch"] == 4
+    import os
+    out = ens.save(os.path.join(str(tmp_path), "ens"), N, D)
+    z = load(out)
+    assert {"fx", "n_it", "f_eval", "problem", "at", "bt"} <= set(z)
+    assert z["at"].shape == (2, N, D, D) and z["bt"].shape == (2, N, D) and list(z["problem"]) == [0, 7]
+    assert np.array_equal(z["at"][1].ravel(), res["kept"][7][:N * D * D])

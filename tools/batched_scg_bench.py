@@ -31,7 +31,7 @@ def main(B=296, model="L96", method="rk2", tf=10.0, max_it=500):
     t_init = time.perf_counter() - t0
     opt = BatchedSCG(ev, {"max_it": max_it, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False})
     t0 = time.perf_counter()
-    X, fx = opt(X0)
+    X, fx = opt(X0, adopt=True)
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     st = opt.stats
@@ -39,7 +39,8 @@ def main(B=296, model="L96", method="rk2", tf=10.0, max_it=500):
                       "init_seconds": round(t_init, 4), "batch_evaluations": int(st["evaluations"]),
                       "iterations_min_median_max": [int(st["MaxIt"].min()), int(np.median(st["MaxIt"])), int(st["MaxIt"].max())],
                       "fx0_mean": float(st["fx"][0].mean()), "fx_mean": float(np.mean(fx)),
-                      "optimisations_per_s": round(B / el, 2),
+                      "optimisations_per_s": round(B / el, 2), "host_syncs": int(st["host_syncs"]),
+                      "device_buffers": 5,
                       "problem_evaluations_per_s": round(B * st["evaluations"] / el, 1)}), flush=True)
     ev.close(); v.close()
 

@@ -68,6 +68,8 @@ def _load():
     lib.vgpa_sync.argtypes = [H]
     lib.vgpa_set_active.restype = C.c_int
     lib.vgpa_set_active.argtypes = [H, C.c_void_p]
+    lib.vgpa_set_active_list.restype = C.c_int
+    lib.vgpa_set_active_list.argtypes = [H, C.c_void_p, C.c_int32]
     lib.vgpa_eval_full.restype = C.c_int
     lib.vgpa_eval_full.argtypes = [H, C.c_int64, _dp, C.POINTER(VgpaFullOut)]
     lib.vgpa_solve_fwd.restype = C.c_int

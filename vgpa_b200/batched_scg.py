@@ -11,8 +11,19 @@ iteration (vgpa_eval_device) and the optimiser's dot products, AXPYs and directi
 updates (vgpa_bdot / baxpy / bdir / bcopy / bstats) -- runs on the device.  PyTorch
 only owns the device buffers.
 
+Memory: FIVE (B, n) buffers -- x, the trial point, the gradient, the trial gradient and the search
+direction (65.6 MB per Lorenz-96 problem).  The reference's grad_old is not kept: it only enters
+through g_new . g_old (taken as trial-gradient . gradient just before the gradient is replaced) and
+through sum |g_old| (a scalar per problem).  Host synchronisations: three per iteration (the
+direction's dot products; the curvature evaluation with its dot product; the trial evaluation with
+every reduction the rest of the iteration can need, computed for all active rows at once).  Thinned-out
+Lorenz-96 ensembles are evaluated through compacted launches (vgpa_set_active_list), so the survivors
+still fill whole waves.  `ShardedBatchedSCG` runs an ensemble over the GPUs of a node in resident
+sub-batches and gathers the results.
+
 Per problem the arithmetic is the reference's, so each problem's `fx` trace follows
-the single-problem SCG (tests/test_gpu_batched_scg.py: 1e-6 on the common prefix).
+the reference's SCG (tests/test_gpu_batched_scg.py: 1e-6 on the common prefix, against the traces
+the unmodified reference recorded).
 """
 import numpy as np
 
@@ -32,22 +43,26 @@ class BatchedSCG:
         self.f_tol = opts.get("f_tol", 1.0e-8)
         self.display = opts.get("display", False)
         self.stats = None
+        self.host_syncs = 0
 
     # -- device helpers ----------------------------------------------------------
-    def _setup(self, X0):
+    def _setup(self, X0, adopt=False):
         import torch
         self.torch = torch
         ev = self.ev
         B, n = ev.B, ev.n_x
         dev = torch.device("cuda", ev.device)
-        X = torch.as_tensor(X0, dtype=torch.float64)
-        if X.dim() == 1:
-            X = X.unsqueeze(0).expand(B, n)
-        self.X = X.to(dev).contiguous().clone()
+        if adopt and isinstance(X0, torch.Tensor) and X0.is_cuda and X0.shape == (B, n) and X0.is_contiguous():
+            self.X = X0                              # the caller's device buffer becomes x (no sixth buffer)
+        else:
+            X = torch.as_tensor(X0, dtype=torch.float64)
+            if X.dim() == 1:
+                X = X.unsqueeze(0).expand(B, n)
+            self.X = X.to(dev).contiguous().clone()
         z = lambda: torch.empty((B, n), dtype=torch.float64, device=dev)
-        self.XT, self.Gn, self.Go, self.GT, self.Dd = z(), z(), z(), z(), z()
+        self.XT, self.Gn, self.GT, self.Dd = z(), z(), z(), z()
         self.Fd = torch.empty(B, dtype=torch.float64, device=dev)
-        self.sc = torch.zeros(3 * B, dtype=torch.float64, device=dev)       # reduction outputs
+        self.sc = torch.zeros(8 * B, dtype=torch.float64, device=dev)       # reduction outputs: dot (3B) | stats (2B) | stats (2B)
         self.coef = torch.empty(B, dtype=torch.float64, device=dev)         # per-problem scalars in
         self.mask = torch.empty(B, dtype=torch.int32, device=dev)
         self.act = torch.ones(B, dtype=torch.int32, device=dev)              # active set of the evaluations
@@ -55,23 +70,37 @@ class BatchedSCG:
         self._actv_ptr = None                                                # None = every row
         self.stream = torch.cuda.current_stream(dev).cuda_stream
         self.B, self.n = B, n
+        self._use_list = ev.model == "L96"
+        self.host_syncs = 0
 
-    def _eval(self, X, G, who=None):
-        """F (host, B) and grad (device) at the rows of X.  `who` (B booleans): the problems that need
-        this evaluation; the kernels skip the others (vgpa_set_active), whose F entries and gradient
-        rows keep their previous content -- every use below is masked by the same condition.  A batch
-        thus stops paying for problems that have converged."""
-        if who is not None and not who.all():
+    def _eval_async(self, X, G, who=None):
+        """Enqueue F (device, self.Fd) and grad at the rows of X.  `who` (B booleans): the problems that
+        need this evaluation; the others are skipped -- Lorenz-96 through a compacted launch list (the
+        survivors fill whole waves), the small models through per-problem flags -- and their F entries
+        and gradient rows keep their previous content (every use below is masked by the same condition)."""
+        ev = self.ev
+        partial = who is not None and not who.all()
+        if partial and self._use_list:
+            ev.set_active(None)
+            ev.set_active_list(np.flatnonzero(who))
+        elif partial:
             self.act.copy_(self.torch.from_numpy(np.ascontiguousarray(who.astype(np.int32))))
-            self.ev.set_active(self.act.data_ptr())
+            ev.set_active(self.act.data_ptr())
         else:
-            self.ev.set_active(None)
+            ev.set_active(None)
+            if self._use_list:
+                ev.set_active_list(None)
+        ev.eval_device(X.data_ptr(), self.n, self.Fd.data_ptr(), G.data_ptr(), self.n, self.stream)
+
+    def _finish_eval(self):
+        """Wait for the enqueued work (one host synchronisation), check the evaluation's status."""
         try:
-            self.ev.eval_device(X.data_ptr(), self.n, self.Fd.data_ptr(), G.data_ptr(), self.n, self.stream)
             self.ev.sync()
         finally:
             self.ev.set_active(None)
-        return self.Fd.cpu().numpy()
+            if self._use_list:
+                self.ev.set_active_list(None)
+        self.host_syncs += 1
 
     def _rows(self, active):
         """Rows the vector kernels below work on: the problems still being optimised (a superset is
@@ -82,11 +111,22 @@ class BatchedSCG:
             self.actv.copy_(self.torch.from_numpy(np.ascontiguousarray(active.astype(np.int32))))
             self._actv_ptr = self.actv.data_ptr()
 
-    def _dot(self, x, y, z=None):
+    def _dot_async(self, x, y, z=None):
+        """sc[0:B] = x.y, sc[B:2B] = x.z, sc[2B:3B] = x.x (enqueued)."""
         raise_for(lib.vgpa_bdot(self.B, self.n, x.data_ptr(), y.data_ptr(), z.data_ptr() if z is not None else None,
                                 self.n, self.sc.data_ptr(), self._actv_ptr, self.stream))
-        r = self.sc.cpu().numpy().reshape(3, self.B)
-        return r[0].copy(), r[1].copy(), r[2].copy()
+
+    def _stats_async(self, x, slot):
+        """sc[(3 + 2 slot) B ...] = max|x|, sum|x| (enqueued); slot 0 or 1."""
+        off = (3 + 2 * slot) * self.B * 8
+        raise_for(lib.vgpa_bstats(self.B, self.n, x.data_ptr(), self.n, self.sc.data_ptr() + off, self._actv_ptr, self.stream))
+
+    def _fetch(self, with_F=False):
+        """The reduction outputs (and F) on the host: (dot3 (3, B), stats0 (2, B), stats1 (2, B)[, F (B,)])."""
+        r = self.sc.cpu().numpy()
+        B = self.B
+        out = (r[:3 * B].reshape(3, B).copy(), r[3 * B:5 * B].reshape(2, B).copy(), r[5 * B:7 * B].reshape(2, B).copy())
+        return out + (self.Fd.cpu().numpy().copy(),) if with_F else out
 
     def _axpy(self, a, x, y, out):
         self.coef.copy_(self.torch.from_numpy(np.ascontiguousarray(a)))
@@ -104,27 +144,27 @@ class BatchedSCG:
         raise_for(lib.vgpa_bdir(self.B, self.n, self.mask.data_ptr(), self.coef.data_ptr(), self.Dd.data_ptr(),
                                 self.Gn.data_ptr(), self.n, self.stream))
 
-    def _maxabs_sumabs(self, x):
-        raise_for(lib.vgpa_bstats(self.B, self.n, x.data_ptr(), self.n, self.sc.data_ptr(), self._actv_ptr, self.stream))
-        r = self.sc.cpu().numpy()[:2 * self.B].reshape(2, self.B)
-        return r[0].copy(), r[1].copy()
-
     # -- the optimiser -------------------------------------------------------------
-    def __call__(self, X0):
+    def __call__(self, X0, adopt=False):
         """Returns (X (B, n) device tensor, fx (B,) numpy).  self.stats holds the per-problem
-        traces: fx, dfx, beta of shape (max_it, B), MaxIt (B,), f_eval, df_eval (B,)."""
-        self._setup(X0)
+        traces: fx, dfx, beta of shape (max_it, B), MaxIt (B,), f_eval, df_eval (B,).
+        adopt=True: a contiguous (B, n) CUDA tensor X0 is optimised in place (no copy of it is made)."""
+        self._setup(X0, adopt)
         B, nit = self.B, self.nit
         eps = np.finfo(float).eps
         st = {"MaxIt": np.full(B, nit), "fx": np.zeros((nit, B)), "dfx": np.zeros((nit, B)),
               "beta": np.zeros((nit, B)), "f_eval": np.zeros(B), "df_eval": np.zeros(B), "evaluations": 0}
         self.stats = st
-        f_now = self._eval(self.X, self.Gn).copy()
+        self._eval_async(self.X, self.Gn)
+        self._stats_async(self.Gn, 0)
+        self._finish_eval()
+        _, s0, _, f_now = self._fetch(True)
         st["evaluations"] += 1
         st["f_eval"] += 1
         st["df_eval"] += 1
         f_old = f_now.copy()
-        self.Go.copy_(self.Gn)
+        sum_gn = s0[1].copy()                                         # sum |grad_new|
+        sum_go = sum_gn.copy()                                        # sum |grad_old| (grad_old = grad_new at the start)
         self._direction(np.full(B, 2), np.zeros(B))                  # d = -grad
         active = np.ones(B, dtype=bool)
         success = np.ones(B, dtype=bool)
@@ -132,7 +172,6 @@ class BatchedSCG:
         beta = np.ones(B)
         kappa, theta, mu = np.zeros(B), np.zeros(B), np.zeros(B)
         fx_out = f_now.copy()
-        dfx_prev = self._maxabs_sumabs(self.Gn)[1]                    # sum |g| of the current gradient
 
         for j in range(nit):
             if not active.any():
@@ -141,12 +180,17 @@ class BatchedSCG:
             S = success & active
             if S.any():
                 # first / second directional derivatives along d  (optim_scg.py:137-170)
-                dg, _, dd = self._dot(self.Dd, self.Gn)
+                self._dot_async(self.Dd, self.Gn)
+                self.host_syncs += 1
+                d3, _, _ = self._fetch()
+                dg, dd = d3[0], d3[2]
                 flip = S & (dg >= 0.0)
                 if flip.any():
                     self._direction(np.where(flip, 2, 0), np.zeros(B))
-                    dg2, _, dd2 = self._dot(self.Dd, self.Gn)
-                    dg, dd = np.where(flip, dg2, dg), np.where(flip, dd2, dd)
+                    self._dot_async(self.Dd, self.Gn)
+                    self.host_syncs += 1
+                    d3, _, _ = self._fetch()
+                    dg, dd = np.where(flip, d3[0], dg), np.where(flip, d3[2], dd)
                 mu = np.where(S, dg, mu)
                 kappa = np.where(S, dd, kappa)
                 tiny = S & (kappa < eps)
@@ -157,12 +201,14 @@ class BatchedSCG:
                     S &= ~tiny
                 sigma = np.where(S, self.SIGMA0 / np.sqrt(np.where(kappa > 0, kappa, 1.0)), 0.0)
                 self._axpy(sigma, self.Dd, self.X, self.XT)           # x_plus = x + sigma d
-                self._eval(self.XT, self.GT, S)                       # df(x_plus, eval_fun=True)
+                self._eval_async(self.XT, self.GT, S)                 # df(x_plus, eval_fun=True)
+                self._dot_async(self.Dd, self.GT)
+                self._finish_eval()
+                d3, _, _ = self._fetch()
                 st["evaluations"] += 1
                 st["f_eval"][S] += 1
                 st["df_eval"][S] += 1
-                dgp, _, _ = self._dot(self.Dd, self.GT)
-                theta = np.where(S, (dgp - mu) / np.where(S, sigma, 1.0), theta)
+                theta = np.where(S, (d3[0] - mu) / np.where(S, sigma, 1.0), theta)
             # effective curvature and step length  (optim_scg.py:173-186)
             delta = theta + beta * kappa
             neg = active & (delta <= 0.0)
@@ -170,7 +216,15 @@ class BatchedSCG:
             beta = np.where(neg, beta - theta / np.where(kappa != 0, kappa, 1.0), beta)
             alpha = np.where(active, -(mu / np.where(delta != 0, delta, 1.0)), 0.0)
             self._axpy(alpha, self.Dd, self.X, self.XT)               # x_new = x + alpha d
-            f_new = self._eval(self.XT, self.GT, active).copy()       # f(x_new); its gradient is kept
+            self._eval_async(self.XT, self.GT, active)                # f(x_new); its gradient is kept
+            # every reduction the rest of the iteration can need, for all active rows, behind the SAME
+            # synchronisation: g_trial . g (the Polak-Ribiere numerator needs g_new . g_old AFTER the move,
+            # i.e. trial gradient . current gradient), g_trial . g_trial, sum |g_trial|, max |d|
+            self._dot_async(self.GT, self.Gn)
+            self._stats_async(self.GT, 0)
+            self._stats_async(self.Dd, 1)
+            self._finish_eval()
+            d3, sGT, sD, f_new = self._fetch(True)
             st["evaluations"] += 1
             st["f_eval"][active] += 1
             # comparison ratio  (optim_scg.py:192-204)
@@ -184,34 +238,32 @@ class BatchedSCG:
             f_now = np.where(succ, f_new, np.where(fail, f_old, f_now))
             # statistics: the reference records sum|g| of the gradient at the PREVIOUS accepted
             # point on success and of grad_old on failure (optim_scg.py:197-209)
-            sum_go = self._maxabs_sumabs(self.Go)[1] if fail.any() else dfx_prev
             st["fx"][j] = np.where(active, f_now, st["fx"][j - 1] if j else f_now)
             st["beta"][j] = beta
-            st["dfx"][j] = np.where(succ, dfx_prev, sum_go)
+            st["dfx"][j] = np.where(succ, sum_gn, sum_go)
             if self.display and j % 10 == 0:
                 print(f" {j}: mean fx={np.mean(f_now):.3f}\tactive={int(active.sum())}")
             # termination and the move to the new point  (optim_scg.py:217-247)
+            move = np.zeros(B, dtype=bool)
+            gg_all = ggo = np.zeros(B)
             if succ.any():
-                maxd, _ = self._maxabs_sumabs(self.Dd)
+                maxd = sD[0]
                 done = succ & (np.abs(alpha) * maxd <= self.x_tol) & (np.abs(f_new - f_old) <= self.f_tol)
                 st["MaxIt"][done] = j + 1
                 fx_out[done] = f_new[done]
                 active &= ~done
                 move = succ & ~done
                 f_old = np.where(move, f_new, f_old)
-                self._copy_where(move, self.Gn, self.Go)              # grad_old = grad_new
-                self._copy_where(move, self.GT, self.Gn)              # grad_new = df(x) (x == x_new)
+                ggo, gg_all = d3[0], d3[2]                            # (new grad_new) . (new grad_old), |new grad_new|^2
+                sum_go = np.where(move, sum_gn, sum_go)               # grad_old = grad_new
+                sum_gn = np.where(move, sGT[1], sum_gn)               # grad_new = df(x) (x == x_new)
+                self._copy_where(move, self.GT, self.Gn)
                 st["f_eval"][move] += 1                               # the reference re-evaluates f(x), df(x)
                 st["df_eval"][move] += 1
-                gg_all, ggo, _ = self._dot(self.Gn, self.Gn, self.Go)
                 zero = move & np.isclose(gg_all, 0.0)
                 st["MaxIt"][zero] = j + 1
                 fx_out[zero] = f_now[zero]
                 active &= ~zero
-                dfx_prev = np.where(move, self._maxabs_sumabs(self.Gn)[1], dfx_prev)
-            else:
-                move = np.zeros(B, dtype=bool)
-                gg_all = ggo = np.zeros(B)
             # scale update  (optim_scg.py:250-257)
             beta = np.where(active & (Delta < 0.25), np.minimum(4.0 * beta, self.BETA_MAX), beta)
             beta = np.where(active & (Delta > 0.75), np.maximum(0.5 * beta, self.BETA_MIN), beta)
@@ -225,4 +277,141 @@ class BatchedSCG:
             if mode.any():
                 self._direction(mode, gamma)
         fx_out = np.where(active, f_old, fx_out)                      # max_it reached: optim_scg.py:281
+        st["host_syncs"] = self.host_syncs
         return self.X, fx_out
+
+
+def save_ensemble(name, output):
+    """Write the results of an ensemble run, keyed like the reference's Simulation.save
+    (src/var_bayes/simulation.py:248-311: one gzip-compressed dataset per key of `output`, scalars as
+    1-D arrays) with a leading problem axis: fx (B,), at (K, N, D, D) / bt (K, N, D) for the K problems
+    whose optimised parameters were kept (`kept`), plus the per-problem optimiser statistics.  HDF5
+    (`<name>.h5`) when h5py is installed, else `<name>.npz` with the same keys; vgpa_b200.simulation.load
+    reads either."""
+    from pathlib import Path
+    stem = str(name).strip().replace(" ", "_")
+    data = {k: np.atleast_1d(v) if np.isscalar(v) else np.asarray(v) for k, v in output.items()}
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is not None:
+        out = Path(stem + ".h5")
+        with h5py.File(out, "w") as fh:
+            for key, val in data.items():
+                fh.create_dataset(key, data=val, shape=val.shape, compression="gzip")
+    else:
+        out = Path(stem + ".npz")
+        np.savez_compressed(out, **data)
+    return out
+
+
+class ShardedBatchedSCG:
+    """An ensemble of `total` independent optimisations over the GPUs of one node (one process per GPU,
+    contiguous blocks of problems as in vgpa_b200.ensemble) in device-resident sub-batches: per sub-batch
+    the starting points come from the on-device initialisation (or from `x0_fn`), BatchedSCG optimises
+    them in place, and only the per-problem results (fx, iteration and evaluation counts, optionally the
+    optimised parameters of selected problems) leave the device.  The one collective is the final gather
+    (NCCL under torch.distributed; no process group: a single GPU).
+
+    make_evaluator(lo, hi) -> BatchEvaluator for the problems [lo, hi) on this rank's device.
+    sub_batch: problems resident at once (None: as many as fit `mem_fraction` of the free HBM with the
+    optimiser's five (B, n) buffers and the evaluator's scratch)."""
+
+    def __init__(self, total, make_evaluator, options=None, sub_batch=None, rank=None, world=None, group=None,
+                 mem_fraction=0.85):
+        from .ensemble import shard_bounds
+        import torch.distributed as dist
+        if rank is None or world is None:
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world = 0, 1
+        self.total, self.rank, self.world, self.group = int(total), rank, world, group
+        self.lo, self.hi = shard_bounds(total, rank, world)
+        self.make_evaluator, self.options = make_evaluator, dict(options or {})
+        self.sub_batch, self.mem_fraction = sub_batch, mem_fraction
+        self.result = None
+
+    def _pick_sub_batch(self, n_x, device, scratch_bytes):
+        import torch
+        free, _ = torch.cuda.mem_get_info(device)
+        per_problem = 5 * 8 * n_x + 64
+        fit = int((free * self.mem_fraction - scratch_bytes) // per_problem)
+        return max(1, fit)
+
+    def run(self, t0=0.0, x0_fn=None, keep=()):
+        """Optimise the local block.  x0_fn(lo, hi, X) fills the (hi - lo, n) device tensor X with starting
+        points (default: the on-device VarGP.initialization).  keep: global problem indices whose optimised
+        x is returned (host).  Returns the dict that `save` writes, identical on every rank (except `kept`
+        entries, which each rank holds for its own problems until the gather)."""
+        import torch
+        import torch.distributed as dist
+        keep = set(int(k) for k in keep)
+        n_local = self.hi - self.lo
+        fx = np.zeros(n_local)
+        n_it = np.zeros(n_local, dtype=np.int64)
+        f_eval = np.zeros(n_local)
+        evaluations, syncs, seconds = 0, 0, 0.0
+        kept = {}
+        import time
+        pos = self.lo
+        sub = self.sub_batch
+        while pos < self.hi:
+            ev = self.make_evaluator(pos, min(self.hi, pos + (sub or (self.hi - pos))))
+            if sub is None:       # decide once, from the first (largest possible) evaluator's shape
+                ev.close()
+                dev = torch.device("cuda", ev.device)
+                # evaluator scratch: 2 (D + D^2) N + N doubles per resident problem, one chunk of at most 888
+                scratch = 8 * ev.N * (2 * ev.D * (ev.D + 1) + 1) * 888
+                sub = min(self.hi - self.lo, self._pick_sub_batch(ev.n_x, dev, scratch))
+                continue
+            b = ev.B
+            dev = torch.device("cuda", ev.device)
+            X = torch.empty((b, ev.n_x), dtype=torch.float64, device=dev)
+            if x0_fn is None:
+                ev.initialization_device(X.data_ptr(), ev.n_x, float(t0), torch.cuda.current_stream(dev).cuda_stream)
+                ev.sync()
+            else:
+                x0_fn(pos, pos + b, X)
+            opt = BatchedSCG(ev, self.options)
+            t_ = time.perf_counter()
+            Xf, fxb = opt(X, adopt=True)
+            torch.cuda.synchronize(dev)
+            seconds += time.perf_counter() - t_
+            sl = slice(pos - self.lo, pos - self.lo + b)
+            fx[sl], n_it[sl], f_eval[sl] = fxb, opt.stats["MaxIt"], opt.stats["f_eval"]
+            evaluations += opt.stats["evaluations"] * b
+            syncs += opt.host_syncs
+            for k in keep:
+                if pos <= k < pos + b:
+                    kept[k] = Xf[k - pos].cpu().numpy()
+            del opt, Xf, X
+            ev.close()
+            torch.cuda.empty_cache()
+            pos += b
+        # gather of the per-problem results (the only collective)
+        def gather(v):
+            if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+                return v
+            from .ensemble import gather_free_energies
+            return gather_free_energies(np.asarray(v, dtype=np.float64), self.total, self.group)
+        out = {"fx": gather(fx), "n_it": gather(n_it.astype(np.float64)).astype(np.int64), "f_eval": gather(f_eval),
+               "rank_seconds": seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
+               "sub_batch": sub, "kept": kept}
+        self.result = out
+        return out
+
+    def save(self, name, N, D):
+        """Rank-local file `<name>_rank<r>` in the reference's key convention (save_ensemble)."""
+        r = self.result
+        ks = sorted(r["kept"])
+        out = {"fx": r["fx"], "n_it": r["n_it"], "f_eval": r["f_eval"], "problem": np.array(ks, dtype=np.int64)}
+        if ks:
+            xs = np.stack([r["kept"][k] for k in ks])
+            if D == 1:
+                out["at"], out["bt"] = xs[:, :N], xs[:, N:]
+            else:
+                out["at"] = xs[:, :N * D * D].reshape(len(ks), N, D, D)
+                out["bt"] = xs[:, N * D * D:].reshape(len(ks), N, D)
+        return save_ensemble(f"{name}_rank{self.rank}", out)

@@ -60,6 +60,11 @@ struct vgpa_handle {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     // host-API staging: two slots of one chunk each
     DevBuf st_x[2], st_g[2], st_F;
+    DevBuf plist2[2];                   // vgpa_set_active_list: compacted list of problem indices (device copies,
+    int plist_flip = 0;                 //   alternating: the evaluation in flight may still read the previous one)
+    cudaStream_t s_aux = nullptr;       //   non-blocking stream of the list upload
+    std::vector<int> plist_host;        // ... and the host copy (error messages name the problem, not the position)
+    int n_list = -1;                    // < 0: no list, every problem
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2]{}, ev_comp[2]{}, ev_d2h[2]{};
     cudaStream_t last_stream = nullptr;
@@ -161,6 +166,26 @@ void run_chunk(vgpa_handle* h, const double* d_x, long long xs, int want_grad, d
     }
 }
 
+// The host-buffer entry points (vgpa_eval, vgpa_eval_full) always serve EVERY problem: the active set
+// and the compacted list installed for vgpa_eval_device are suspended for the call (a masked problem
+// would otherwise return whatever the staging buffers hold), and a device evaluation still pending on
+// the caller's stream is waited for first (it shares the scratch and the status words).
+struct HostCallScope {
+    vgpa_handle* h;
+    const int *active, *plist;
+    explicit HostCallScope(vgpa_handle* h_) : h(h_), active(h_->batch.active), plist(h_->batch.plist)
+    {
+        if (h->status_dirty) cudaStreamSynchronize(h->last_stream);
+        h->batch.active = nullptr;
+        h->batch.plist = nullptr;
+    }
+    ~HostCallScope()
+    {
+        h->batch.active = active;
+        h->batch.plist = plist;
+    }
+};
+
 int check_status(vgpa_handle* h)
 {
     if (!h->status_dirty) return VGPA_OK;
@@ -168,9 +193,12 @@ int check_status(vgpa_handle* h)
     std::vector<int> st(h->d.B);
     CK(cudaMemcpy(st.data(), h->status.p, sizeof(int) * h->d.B, cudaMemcpyDeviceToHost), "cudaMemcpy(status)");
     for (int p = 0; p < h->d.B; ++p)
-        if (st[p] != 0)
+        if (st[p] != 0) {
+            // under a compacted launch the status words are indexed by launch position
+            const int prob = (h->n_list >= 0 && p < (int)h->plist_host.size()) ? h->plist_host[p] : p;
             return h->fail(VGPA_ENOTPD, "Matrix is not positive definite: S(t) of problem %d at time index %d",
-                           p, st[p] - 1);
+                           prob, st[p] - 1);
+        }
     return VGPA_OK;
 }
 
@@ -356,8 +384,9 @@ void vgpa_destroy(vgpa_handle* h)
     for (DevBuf* b : {&h->theta, &h->sigma, &h->R, &h->obs_t, &h->obs_index, &h->obs_y, &h->m0, &h->s0, &h->E0,
                       &h->status, &h->sc_mt, &h->sc_st, &h->sc_dEm, &h->sc_dEs, &h->sc_esde, &h->sc2_mt, &h->sc2_st,
                       &h->sc2_dEm, &h->sc2_dEs, &h->sc2_esde, &h->st_x[0],
-                      &h->st_x[1], &h->st_g[0], &h->st_g[1], &h->st_F})
+                      &h->st_x[1], &h->st_g[0], &h->st_g[1], &h->st_F, &h->plist2[0], &h->plist2[1]})
         b->release();
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
     for (int q = 0; q < 2; ++q) {
         if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
         if (h->ev_comp[q]) cudaEventDestroy(h->ev_comp[q]);
@@ -394,13 +423,14 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * h->d.B, st), "cudaMemsetAsync(status)");
     Extra ex{};
+    const int total = (h->n_list >= 0 && h->batch.plist != nullptr) ? h->n_list : h->d.B;   // launch positions
     if (h->lanes == 2) {
         CK(cudaEventRecord(h->ev_fork, st), "cudaEventRecord");
         CK(cudaStreamWaitEvent(h->s_lane[0], h->ev_fork, 0), "cudaStreamWaitEvent");
         CK(cudaStreamWaitEvent(h->s_lane[1], h->ev_fork, 0), "cudaStreamWaitEvent");
         int ci = 0;
-        for (int p0 = 0; p0 < h->d.B; p0 += h->chunk, ++ci) {
-            const int count = std::min(h->chunk, h->d.B - p0);
+        for (int p0 = 0; p0 < total; p0 += h->chunk, ++ci) {
+            const int count = std::min(h->chunk, total - p0);
             run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, h->s_lane[ci & 1], ci & 1);
         }
         for (int q = 0; q < 2; ++q) {
@@ -408,8 +438,8 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
             CK(cudaStreamWaitEvent(st, h->ev_join[q], 0), "cudaStreamWaitEvent");
         }
     } else {
-        for (int p0 = 0; p0 < h->d.B; p0 += h->chunk) {
-            const int count = std::min(h->chunk, h->d.B - p0);
+        for (int p0 = 0; p0 < total; p0 += h->chunk) {
+            const int count = std::min(h->chunk, total - p0);
             run_chunk(h, d_x, x_stride, want_grad, d_F, d_grad, grad_stride, p0, count, ex, st);
         }
     }
@@ -423,6 +453,40 @@ int vgpa_set_active(vgpa_handle* h, const int32_t* d_active)
 {
     if (!h) return VGPA_EINVAL;
     h->batch.active = d_active;
+    return VGPA_OK;
+}
+
+int vgpa_set_active_list(vgpa_handle* h, const int32_t* list, int32_t n)
+{
+    if (!h) return VGPA_EINVAL;
+    if (list == nullptr || n < 0) {
+        h->n_list = -1;
+        h->batch.plist = nullptr;
+        h->plist_host.clear();
+        return VGPA_OK;
+    }
+    if (h->batch.model != MODEL_L96)
+        return h->fail(VGPA_EINVAL, "vgpa_set_active_list: compacted launches exist for the D = 40 kernels only "
+                                    "(use vgpa_set_active for the small models)");
+    if (n > h->d.B) return h->fail(VGPA_EINVAL, "vgpa_set_active_list: %d entries for %d problems", (int)n, h->d.B);
+    for (int k = 0; k < n; ++k)
+        if (list[k] < 0 || list[k] >= h->d.B)
+            return h->fail(VGPA_EINVAL, "vgpa_set_active_list: entry %d = %d outside [0, %d)", k, (int)list[k], h->d.B);
+    CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    // Upload on a private non-blocking stream into the buffer the evaluation in flight does NOT read: the call
+    // waits for its own tiny copy only, never for the kernels already enqueued on the caller's stream.
+    h->plist_flip ^= 1;
+    DevBuf& buf = h->plist2[h->plist_flip];
+    const size_t bytes = sizeof(int) * (size_t)std::max(h->d.B, 1);
+    if (buf.bytes < bytes) CK(buf.alloc(bytes), "cudaMalloc(list)");
+    if (h->s_aux == nullptr) CK(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (n > 0) {
+        CK(cudaMemcpyAsync(buf.p, list, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->s_aux), "cudaMemcpyAsync(list)");
+        CK(cudaStreamSynchronize(h->s_aux), "cudaStreamSynchronize");
+    }
+    h->plist_host.assign(list, list + n);
+    h->n_list = n;
+    h->batch.plist = buf.as<int>();
     return VGPA_OK;
 }
 
@@ -444,6 +508,7 @@ int vgpa_eval(vgpa_handle* h, const double* x, int64_t x_stride, int want_grad, 
     if (want_grad && h->d.B > 1 && grad_stride < h->n_x)
         return h->fail(VGPA_EINVAL, "grad_stride %lld < %lld", (long long)grad_stride, h->n_x);
     CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    HostCallScope scope(h);
     const int B = h->d.B, C = h->chunk;
     const long long nx = h->n_x;
     const bool shared_x = (x_stride == 0);
@@ -513,6 +578,7 @@ int vgpa_eval_full(vgpa_handle* h, int64_t problem, const double* x, const vgpa_
     if (x == nullptr || out == nullptr) return h->fail(VGPA_EINVAL, "x / out is NULL");
     if (problem < 0 || problem >= h->d.B) return h->fail(VGPA_EINVAL, "problem index %lld out of range", (long long)problem);
     CK(cudaSetDevice(h->d.device), "cudaSetDevice");
+    HostCallScope scope(h);
     const long long nx = h->n_x, N = h->d.N, D = h->d.D, nv = N * D, nm = N * D * D;
     DevBuf dx, dg, dF, dl, dp, def, dedf, dparts;
     auto cleanup = [&]() { for (DevBuf* b : {&dx, &dg, &dF, &dl, &dp, &def, &dedf, &dparts}) b->release(); };

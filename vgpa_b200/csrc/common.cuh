@@ -24,7 +24,13 @@ struct Batch {
     const double* E0;     long long E0_stride;
     const int* active;        // B flags or null: problems whose flag is 0 are skipped by every kernel
                               // (their F, gradient and scratch rows are left untouched)
+    const int* plist;         // or null.  Compacted launches of the D = 40 kernels (vgpa_set_active_list): the
+                              // pass covers list positions [p0, p0 + count) and the problem at position k is
+                              // plist[k], so that a thinned-out ensemble still fills whole waves
 };
+
+// problem served by launch position `pos` (= p0 + local index)
+__device__ __forceinline__ int problem_at(const Batch& b, int pos) { return b.plist != nullptr ? b.plist[pos] : pos; }
 
 // Per-pass (chunk) scratch: trajectories of the marginal moments, the SDE-energy
 // gradients and the per-time-step energy.  Problem-major: [p][t][...].

@@ -418,7 +418,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = b.N;
-    const int lp = blockIdx.x / N, t = blockIdx.x - lp * N, p = p0 + lp;
+    const int lp = blockIdx.x / N, t = blockIdx.x - lp * N, p = problem_at(b, p0 + lp);
     if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const double* At = x + (long long)p * xs + (long long)t * D * D;
     const double* bt = x + (long long)p * xs + (long long)N * D * D + (long long)t * D;
@@ -468,7 +468,7 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             } else if (tid == 3 * D) {
                 const unsigned tq = (unsigned)(t + AHEAD) / (unsigned)N;      // 32-bit: no 64-bit division sequence
                 const int lpn = lp + (int)tq, tn = t + AHEAD - (int)tq * N;
-                bulk_prefetch_l2(x + (long long)(p0 + lpn) * xs + (long long)tn * D * D, D * ROWB);
+                bulk_prefetch_l2(x + (long long)problem_at(b, p0 + lpn) * xs + (long long)tn * D * D, D * ROWB);
             }
         }
     }

@@ -164,7 +164,7 @@ l96_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, i
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int irow = 8 * w + g;
-    const int lp = blockIdx.x, p = p0 + lp, N = b.N;
+    const int lp = blockIdx.x, p = problem_at(b, p0 + lp), N = b.N;
     if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const double* A = x + (long long)p * xs;
     const double* bo = A + (long long)N * D * D;
@@ -379,17 +379,19 @@ l96_bwd_kernel(Batch b, BwdArgs a, int p0)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int irow = 8 * w + g;   // the matrix / vector row of this lane
-    const int lp = blockIdx.x, p = p0 + lp, N = b.N;
+    const int lp = blockIdx.x, p = problem_at(b, p0 + lp), N = b.N;
     if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
-    const double* A = a.A + (long long)lp * a.xs;
-    const double* bo = a.bo ? a.bo + (long long)lp * a.xs : nullptr;
+    // x and the gradient are addressed by PROBLEM (a.A, a.gA point at problem p0), the scratch by launch position
+    const long long xrow = (long long)(p - p0);
+    const double* A = a.A + xrow * a.xs;
+    const double* bo = a.bo ? a.bo + xrow * a.xs : nullptr;
     const double* mt = a.mt ? a.mt + (long long)lp * a.traj_v : nullptr;
     const double* st = a.st ? a.st + (long long)lp * a.traj_m : nullptr;
     const double* dEm = a.dEm + (long long)lp * a.traj_v;
     const double* dEs = a.dEs + (long long)lp * a.traj_m;
     const bool with_grad = a.gA != nullptr;
-    double* gA = with_grad ? a.gA + (long long)lp * a.gs : nullptr;
-    double* gb = with_grad ? a.gb + (long long)lp * a.gs : nullptr;
+    double* gA = with_grad ? a.gA + xrow * a.gs : nullptr;
+    double* gb = with_grad ? a.gb + xrow * a.gs : nullptr;
     const bool dense = a.jm_dense != nullptr;
     const bool keep = a.lam_out != nullptr && lp == 0;
     const double* oy = dense ? nullptr : b.obs_y + p * b.obs_y_stride;

@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(128)
 finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, Extra ex)
 {
     __shared__ double sh[128];
-    const int lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
+    const int lp = blockIdx.x, p = problem_at(b, p0 + lp), tid = threadIdx.x;
     if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
     const int N = b.N, D = b.D, M = b.M, DD = D * D;
     // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)

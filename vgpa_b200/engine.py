@@ -128,6 +128,15 @@ class BatchEvaluator:
         its F and gradient row stay untouched), or None for every problem."""
         raise_for(lib.vgpa_set_active(self._h, mask_ptr), self._h)
 
+    def set_active_list(self, problems=None):
+        """Compacted launches (Lorenz-96 only): evaluate exactly these problem indices in the following
+        eval_device calls, chunked by list position -- a thinned-out ensemble keeps whole waves.  None: off."""
+        if problems is None:
+            raise_for(lib.vgpa_set_active_list(self._h, None, -1), self._h)
+            return
+        lst = np.ascontiguousarray(problems, dtype=np.int32)
+        raise_for(lib.vgpa_set_active_list(self._h, lst.ctypes.data, int(lst.size)), self._h)
+
     def initialization(self, t0=0.0):
         """VarGP.initialization for every problem of the batch, computed on the GPU: (B, n_x) host array."""
         X = np.empty((self.B, self.n_x))
