@@ -22,6 +22,8 @@ H2D + D2H copies running concurrently: the ceiling the host-buffer API can reach
 JSON keys follow the driver contract; see DESIGN.md section "Measurement".
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -221,6 +223,48 @@ def reference_python_rate(override=None):
             "F_x0": float(F), "gnorm_x0": float(np.linalg.norm(g)), "x0": x0, "grad": g}
 
 
+def cpu_port_scg_rate(threads, fam):
+    """The same ensemble OPTIMISATION on the host cores: one problem per thread, the reference's own SCG
+    (baseline/_ref: src/numerics/optim_scg.py) driving the C port's free energy + gradient (one evaluation
+    per distinct x, as VarGP's cache gives the CUDA path).  Bounded sample: `threads` problems."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import Oracle, Problem
+    try:
+        from baseline.refload import import_reference
+        SCG = import_reference()["SCG"]
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    orc = Oracle()
+
+    def one(k):
+        s_ = fam["sets"][k % len(fam["sets"])]
+        prob = Problem(model="L96", method="rk2", D=D, N=N_GRID, dt=DT, theta=np.array([8.0]),
+                       sigma=np.full(D, fam["noise"][k % N_NOISE]), R=np.ones(D), obs_t=fam["obs_t"], obs_y=s_["obs_y"],
+                       m0=s_["m0"], s0=fam["s0"], E0=s_["E0"], dt_model=fam["dt_model"])
+        rng = np.random.default_rng([SEED, 77, k])
+        x0 = s_["x0"] * (1.0 + 0.02 * rng.uniform(-1, 1, N_X))
+        last = {"x": None}
+
+        def both(x):
+            if last["x"] is None or not np.array_equal(x, last["x"]):
+                last["F"], last["g"] = orc.eval(prob, x)
+                last["x"] = x.copy()
+                last["n"] = last.get("n", 0) + 1
+            return last
+        opt = SCG(lambda x: float(both(x)["F"]), lambda x, eval_fun=False: both(x)["g"].copy(),
+                  {"max_it": 500, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False})
+        _, fx = opt(x0)
+        return int(opt.stats["MaxIt"]), last["n"], float(fx)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):      # the optimiser's own messages (redirected once, not per thread)
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            res = list(ex.map(one, range(threads)))
+    el = time.perf_counter() - t0
+    return {"optimisations_per_s": threads / el, "problems": threads, "threads": threads, "seconds": el,
+            "iterations_median": int(np.median([r[0] for r in res])), "port_evaluations": int(sum(r[1] for r in res)),
+            "what": "reference SCG (baseline/_ref) over the C port's evaluation, one problem per host thread"}
+
+
 METRIC = "free-energy+grad evals/sec (L96 D=40, T=1000); batched problems/sec"
 WORKLOAD = ("L96 D=40 N=1001 (T=1000) RK2 ensemble: 8 obs sets x 32 starts x 16 noise values per GPU "
             "(BASELINE configs[4])")
@@ -259,6 +303,8 @@ def run_reference(args):
         cal.pop("x0", None)
         cal.pop("grad", None)
         line["cpu_baseline_reference"] = cal
+    if args.gpus == 1 and args.scg_problems > 0:
+        line["ensemble_scg"] = cpu_port_scg_rate(threads, fam)
     print(json.dumps(line), flush=True)
 
 
@@ -300,6 +346,57 @@ def copy_ceiling(torch, dist, dev, world, nbytes=1 << 30, reps=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     del d_in, d_out, h_in, h_out
     return world * reps * nbytes / (float(t.item()) * 1e-3) / 1e9
+
+
+def ensemble_scg(torch, dist, dev, local, rank, world, fam, per_gpu):
+    """What BASELINE configs[4] describes in full: every member of the ensemble OPTIMISED (SCG to convergence),
+    device-resident, sharded over the GPUs -- vgpa_b200.batched_scg.ShardedBatchedSCG on `per_gpu` members
+    of each rank's shard (multi-start x noise sweep of the first observation sets), starting points
+    x0 * (1 + 0.02 u) generated in HBM.  Whole-job optimisations/s, timed on the host around the sharded
+    run (it ends in the NCCL gather), max over ranks."""
+    from vgpa_b200.batched_scg import ShardedBatchedSCG
+    from vgpa_b200.engine import BatchEvaluator
+    iset, arr = shard_arrays(fam, per_gpu)
+
+    def make(lo, hi):
+        a, b_ = lo - rank * per_gpu, hi - rank * per_gpu
+        return BatchEvaluator("L96", "rk2", N_GRID, DT, [8.0], arr["sigma"][a:b_], np.ones(D), fam["obs_t"],
+                              arr["obs_y"][a:b_], arr["m0"][a:b_], fam["s0"], arr["E0"][a:b_], B=b_ - a,
+                              dt_model=fam["dt_model"], device=local)
+
+    x0s = torch.from_numpy(np.stack([s_["x0"] for s_ in fam["sets"]])).to(dev)
+
+    def x0_fn(lo, hi, X):
+        a = lo - rank * per_gpu
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(SEED % (2 ** 31) + 1000 + lo)
+        for p0 in range(0, hi - lo, 64):
+            p1 = min(hi - lo, p0 + 64)
+            u = torch.rand((p1 - p0, N_X), dtype=torch.float64, device=dev, generator=gen) * 2.0 - 1.0
+            X[p0:p1] = x0s[torch.from_numpy(iset[a + p0:a + p1]).to(dev)] * (1.0 + 0.02 * u)
+    ens = ShardedBatchedSCG(per_gpu * world, make, {"max_it": 500, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False},
+                            rank=rank, world=world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = ens.run(x0_fn=x0_fn)
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    useful = torch.tensor([float(res["f_eval"][rank * per_gpu:(rank + 1) * per_gpu].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(useful, op=dist.ReduceOp.SUM)
+    el = float(el.item())
+    assert np.all(np.isfinite(res["fx"]))
+    return {"optimisations_per_s": per_gpu * world / el, "problems": per_gpu * world, "problems_per_gpu": per_gpu,
+            "seconds": el, "iterations_min_median_max": [int(res["n_it"].min()), int(np.median(res["n_it"])), int(res["n_it"].max())],
+            "f_evaluations_per_s": float(useful.item()) / el,
+            "resident_sub_batch": int(res["sub_batch"]), "device_buffers_per_problem": 5,
+            "host_syncs_per_iteration": round(res["rank_host_syncs"] / max(int(res["n_it"][rank * per_gpu:(rank + 1) * per_gpu].max()), 1), 2),
+            "fx_mean": float(np.mean(res["fx"])),
+            "what": "SCG to convergence (max_it 500, x_tol 1e-6, f_tol 1e-8) of every ensemble member, device-resident; "
+                    "f_evaluations counts the reference's f(x) calls (optim_scg.py stats['f_eval'])"}
 
 
 def secondary_configs(torch, local, hbm_peak):
@@ -616,6 +713,9 @@ def run_b200(args):
     ge.free()
 
     ceiling = copy_ceiling(torch, dist, dev, world)
+    scg_line = None
+    if args.scg_problems > 0:
+        scg_line = ensemble_scg(torch, dist, dev, local, rank, world, fam, args.scg_problems)
     if rank == 0:
         e2e_gbs = e2e_val * N_X * 8.0 / 1e9           # per direction: x in, gradient out
         line["e2e"] = {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(Be * N_X * 8),
@@ -656,6 +756,8 @@ def run_b200(args):
                     line["secondary"] = secondary_configs(torch, local, hbm_peak)
                 except Exception as e:      # never lose the headline line to a secondary measurement
                     line["secondary"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if scg_line is not None:
+            line["ensemble_scg"] = scg_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -673,6 +775,8 @@ def main():
     ap.add_argument("--no-python-reference", action="store_true",
                     help="skip the one warm evaluation of the unmodified Python reference (about a minute of CPU)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (N = 1 only)")
+    ap.add_argument("--scg-problems", type=int, default=444,
+                    help="problems per GPU of the device-resident ensemble OPTIMISATION (secondary key ensemble_scg; 0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -19,7 +19,7 @@ def run(env_extra, *args):
 
 
 def test_reference_arm_line():
-    r = run({}, "--steps", "1", "--warmup", "0")
+    r = run({}, "--steps", "1", "--warmup", "0", "--scg-problems", "0")      # (the SCG sample alone is a minute of CPU)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
