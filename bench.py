@@ -499,6 +499,16 @@ def secondary_configs(torch, local, hbm_peak):
                            "cuda_evaluations": int(v.n_eval - n0),
                            "reference_seconds": "about 18 minutes on the authoring container (tests/golden/scg_L96_full.npz)"}
     v.close()
+    # the same optimisation with the optimiser's vectors resident in HBM (Simulation.run(optimizer="device"))
+    sim2 = Simulation("bench")
+    sim2.setup(l96_params())
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim2.run(max_it=500, display=False, optimizer="device")
+    el = time.perf_counter() - t0
+    out["L96_full_scg_device_optimizer"] = {"seconds": round(el, 3), "iterations": int(sim2.scg_stats["MaxIt"]),
+                                            "fx": float(sim2.output["fx"]),
+                                            "includes": "initialisation, optimisation, final evaluation with all trajectories"}
     return out
 
 

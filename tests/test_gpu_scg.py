@@ -166,3 +166,24 @@ def test_gradient_arrays_are_owned_by_the_caller():
     del view, many
     gc.collect()
     assert pool._closed and pool._free == []
+
+
+@pytest.mark.parametrize("model", ["DW", "L63"])
+def test_simulation_run_with_device_optimizer(model, capsys):
+    """Simulation.run(optimizer="device"): the whole optimisation resident on the GPU (BatchedSCG, batch of
+    one) must reproduce the reference's recorded trace like the host loop does, and fill the same outputs."""
+    from vgpa_b200 import Simulation
+    g = np.load(GOLDEN / f"scg_{model}.npz")
+    method, tf = JOBS[model]
+    sim = Simulation("t")
+    sim.setup(mg.config(model, method, tf))
+    sim.run(max_it=int(g["max_it"]), display=False, optimizer="device")
+    capsys.readouterr()
+    st = sim.scg_stats
+    n_ref, n_new = int(g["n_it"]), int(st["MaxIt"])
+    n = min(n_ref, n_new)
+    assert abs(n_ref - n_new) <= max(2, n_ref // 50), (n_ref, n_new)
+    ref, new = g["trace_fx"][:n], st["fx"][:n]
+    assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6
+    assert abs(sim.output["fx"] - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0)
+    assert {"at", "bt", "fx", "m0", "s0", "mt", "st", "Efx", "Edf", "lamt", "psit"} <= set(sim.output)

@@ -85,14 +85,32 @@ class Simulation(object):
         return VarGP(md["model"], md["m0"], md["s0"], fwd, bwd, lik, kl0, md["obs_y"], md["obs_t"],
                      device=self.device)
 
-    def run(self, max_it=500, display=True):
-        """simulation.py:180-267"""
+    def run(self, max_it=500, display=True, optimizer="host"):
+        """simulation.py:180-267.  optimizer="host": the SCG loop on the host, as in the reference (13 MB
+        numpy vectors per operation at the Lorenz-96 shape, x and grad F crossing PCIe at every evaluation);
+        optimizer="device": the same optimiser with x, the gradients and the search direction resident in
+        HBM (vgpa_b200.batched_scg.BatchedSCG with a batch of one) -- the same trace to 1e-6
+        (tests/test_gpu_scg.py), without the host vector arithmetic and the transfers."""
         vgpa = self.build()
         options = {"max_it": max_it, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": display}
-        optimize = SCG(vgpa.free_energy, vgpa.gradient, options)
         x0 = vgpa.initialization()
         t0 = time.perf_counter()
-        x, fx = optimize(x0.copy())
+        if optimizer == "device":
+            from .batched_scg import BatchedSCG
+            optimize = BatchedSCG(vgpa._ev, options)
+            X, fxs = optimize(x0)
+            x, fx = X[0].cpu().numpy(), float(fxs[0])
+            n = int(optimize.stats["MaxIt"][0])
+            self.scg_stats = {"MaxIt": n, "fx": optimize.stats["fx"][:, 0].copy(), "dfx": optimize.stats["dfx"][:, 0].copy(),
+                              "beta": optimize.stats["beta"][:, 0].copy(), "f_eval": float(optimize.stats["f_eval"][0]),
+                              "df_eval": float(optimize.stats["df_eval"][0])}
+            del optimize, X
+        elif optimizer == "host":
+            optimize = SCG(vgpa.free_energy, vgpa.gradient, options)
+            x, fx = optimize(x0.copy())
+            self.scg_stats = optimize.stats
+        else:
+            raise ValueError(f" Simulation.run: unknown optimizer {optimizer!r} (host, device).")
         print(f" Elapsed time: {(time.perf_counter() - t0):.2f} seconds.")
         md = self.m_data
         if md["model"].single_dim:
@@ -105,7 +123,6 @@ class Simulation(object):
         self.output["fx"] = fx
         vgpa.free_energy(x)            # make the cached state the one of the returned x
         self.output.update(vgpa.arg_out)
-        self.scg_stats = optimize.stats
         vgpa.close()
 
     def save(self):
