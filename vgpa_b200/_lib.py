@@ -5,12 +5,13 @@ There is no CPU fallback: if the CUDA library has not been built the import of
 this module fails loudly, and every call needs a B200 (sm_100a) device.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libvgpa_b200.so"
+LIB_PATH = Path(os.environ["VGPA_LIB"]) if os.environ.get("VGPA_LIB") else PKG / "libvgpa_b200.so"   # override: kernel A/B runs
 
 VGPA_OK, VGPA_EINVAL, VGPA_ENOTPD, VGPA_ECUDA = 0, 1, 2, 3
 MODELS = {"DW": 0, "OU": 1, "L63": 2, "L96": 3}
