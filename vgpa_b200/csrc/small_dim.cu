@@ -13,6 +13,7 @@
 //   gradient        src/var_bayes/variational.py:202-334
 //   F               variational.py:199, utilities.py:144-201, gaussian_like.py:69-153
 #include "common.cuh"
+#include "l63_grad.cuh"
 
 namespace vgpa {
 
@@ -429,7 +430,9 @@ __device__ __forceinline__ void drift_moments(const double* th, const double* m,
         Edf[0] = -th[0];
     } else {  // lorenz_63.py:319-326 (reads S[2,0] and S[1,0])
         const double vS = th[0], vR = th[1], vB = th[2];
-        Ef[0] = vS * (m[1] - m[0]);
+        // (__dmul_rn: the product must not be contracted into whatever consumes <f>_0 -- the lane-parallel
+        // kernels of l63_lanes.cu evaluate the same expressions and must give the same bits)
+        Ef[0] = __dmul_rn(vS, m[1] - m[0]);
         Ef[1] = vR * m[0] - m[1] - S[2 * D + 0] - m[0] * m[2];
         Ef[2] = S[1 * D + 0] + m[0] * m[1] - vB * m[2];
         Edf[0] = -vS;        Edf[1] = vS;   Edf[2] = 0.0;
@@ -573,6 +576,22 @@ __device__ __forceinline__ void grad_at(const double* th, const double* isg, dou
                                         double* gA, double* gb)
 {
     constexpr int DD = D * D;
+    if (MODEL == MODEL_L63) {   // explicit rounding, shared with the lane-parallel kernel (l63_grad.cuh)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double mm[3] = {m[0], m[1], m[2]};
+            const double Ar[3] = {At[i * 3 + 0], At[i * 3 + 1], At[i * 3 + 2]};
+            const double Pr[3] = {Psi[i * 3 + 0], Psi[i * 3 + 1], Psi[i * 3 + 2]};
+            const L63Row r = l63_row_terms(i, th[0], th[1], th[2], mm, (i == 1) ? S[6] : S[3], Ar, bt[i], isg[i]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double Sc[3] = {S[j], S[3 + j], S[6 + j]};
+                gA[i * 3 + j] = l63_grad_a(r, Sc, Pr, m[j], lam[i], dtm);
+            }
+            gb[i] = l63_grad_b(r, lam[i], dtm);
+        }
+        return;
+    }
     double Ef[D], Edf[DD], db[D];
     drift_moments<MODEL, D>(th, m, S, Ef, Edf);
 #pragma unroll
@@ -923,6 +942,7 @@ void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long lo
                       int count, cudaStream_t st)
 {
     if (b.D == 1) fwd_dispatch<1>(b, s, x, xs, p0, count, st);
+    else if (l63_lanes_applies(b, count)) launch_l63_fwd_lanes(b, s, x, xs, p0, count, st);
     else          fwd_dispatch<3>(b, s, x, xs, p0, count, st);
 }
 
@@ -953,6 +973,10 @@ void launch_small_bwd(const Batch& b, const Scratch& s, const double* x, long lo
                       long long gs, int p0, int count, const Extra& ex, cudaStream_t st)
 {
     SmallBwdArgs a{x, xs, g, gs, nullptr, nullptr};
+    if (g != nullptr && ex.lamt == nullptr && l63_lanes_applies(b, count)) {
+        launch_l63_bwd_lanes(b, s, x, xs, g, gs, p0, count, st);
+        return;
+    }
     if (b.model == MODEL_DW)      bwd_dispatch<MODEL_DW, 1>(b, s, a, p0, count, ex, st);
     else if (b.model == MODEL_OU) bwd_dispatch<MODEL_OU, 1>(b, s, a, p0, count, ex, st);
     else                          bwd_dispatch<MODEL_L63, 3>(b, s, a, p0, count, ex, st);
