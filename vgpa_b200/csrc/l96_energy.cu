@@ -67,7 +67,6 @@ __device__ unsigned long long g_prof[32];
 
 constexpr int D = 40;
 constexpr int MAT = SM_MAT;         // skewed layout of common.cuh (sm_idx): every access shape conflict-free
-constexpr int ROWB = D * 8;
 constexpr int K = 2 * D + 1;        // sigma points
 
 constexpr int NTH = 128;
@@ -456,22 +455,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
         }
     }
     cp_async_commit();
-    // pull the inputs of the item that will follow this one in its SM slot (148 SMs x 5 CTAs
-    // further down the grid) into L2: its load phase then sees L2 instead of HBM latency
-    {
-        constexpr int AHEAD = 148 * 5;
-        const long long nb = (long long)blockIdx.x + AHEAD;
-        if (nb < (long long)gridDim.x) {
-            if (tid >= 2 * D && tid < 3 * D) {
-                const int r = tid - 2 * D;
-                bulk_prefetch_l2(s.st + nb * (D * D) + r * D, 64 * ((r >> 3) + 1));
-            } else if (tid == 3 * D) {
-                const unsigned tq = (unsigned)(t + AHEAD) / (unsigned)N;      // 32-bit: no 64-bit division sequence
-                const int lpn = lp + (int)tq, tn = t + AHEAD - (int)tq * N;
-                bulk_prefetch_l2(x + (long long)problem_at(b, p0 + lpn) * xs + (long long)tn * D * D, D * ROWB);
-            }
-        }
-    }
+    // (An L2 prefetch of the item that will follow this one in its SM slot was here in round 1; without it
+    // the kernel is 4 % faster: 365 instructions per item for lines that arrive in time anyway.)
     // while the copies fly: zero the strict upper tiles of the L buffer (the copies do not touch
     // them; the residual phase reads whole columns), 1 / sigma
     {
@@ -603,14 +588,8 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             qwrap = fma(sgn_q, l0n, sm.mv[0]);
         }
         double vp = 0.0, vq = 0.0;
-#pragma unroll 2
-        for (int i = i0; i < i1; ++i) {
-            double pp1 = pwrap, qp1 = qwrap;
-            if (i + 1 < D) {
-                const double l1 = Lc[sm_idx(i + 1, 0)], m1 = sm.mv[i + 1];
-                pp1 = fma(sd, l1, m1);
-                qp1 = fma(-sd, l1, m1);
-            }
+        // one row: x[i+1] of both signs given, the residuals of row i accumulate, the windows slide
+        auto row = [&](int i, double pp1, double qp1) {
             const double al = sd * ALc[sm_idx(i, 0)], cvi = sm.cv[i], isg = sm.isg[i];
             const double rp_ = fma(pp1 - pm2, pm1, -p0) + (cvi + al);           // lorenz_96.py:85-101 (theta is in cv)
             const double rq_ = fma(qp1 - qm2, qm1, -q0) + (cvi - al);
@@ -618,7 +597,14 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
             vq = fma(isg * rq_, rq_, vq);
             pm2 = pm1; pm1 = p0; p0 = pp1;
             qm2 = qm1; qm1 = q0; q0 = qp1;
+        };
+        const int ilast = (seg == 2) ? D - 1 : i1;      // rows below ilast have their x[i+1] in the thread's own column
+#pragma unroll 2
+        for (int i = i0; i < ilast; ++i) {
+            const double l1 = Lc[sm_idx(i + 1, 0)], m1 = sm.mv[i + 1];
+            row(i, fma(sd, l1, m1), fma(-sd, l1, m1));
         }
+        if (seg == 2) row(D - 1, pwrap, qwrap);
         if (centre) {
             sm.varp[seg][0] = vp;
         } else {

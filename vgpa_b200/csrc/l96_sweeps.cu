@@ -98,10 +98,13 @@ __device__ __forceinline__ double pick(double c, double n)
     return KIND == K_CUR ? c : (KIND == K_NEXT ? n : 0.5 * (c + n));
 }
 
-// every warp issues the bulk copies of its own 8 rows of a 40 x 40 matrix
+// every warp issues the bulk copies of its own 8 rows of a 40 x 40 matrix: the two rows of a row PAIR are
+// contiguous in the skewed layout (sm_idx: offsets 0 and 40 of an 84-double group) as they are in HBM, so
+// four 640-byte copies do (the bulk-copy instruction is what costs: eight 320-byte copies per warp and
+// matrix were 9 % of the backward sweep's issued instructions)
 __device__ __forceinline__ void load_rows(double* dst, const double* src, uint64_t* bar, int w, int lane)
 {
-    if (lane < 8) bulk_g2s(dst + sm_idx(8 * w + lane, 0), src + (8 * w + lane) * D, ROWB, bar);
+    if (lane < 4) bulk_g2s(dst + sm_idx(8 * w + 2 * lane, 0), src + (8 * w + 2 * lane) * D, 2 * ROWB, bar);
 }
 
 // ===========================================================================
