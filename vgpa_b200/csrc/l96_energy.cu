@@ -430,8 +430,10 @@ l96_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs
     PROF_INIT();
     if (tid == 0) sm.bad = 0;
     // S(t) (lower block triangle), A(t), m(t), b(t) by 16-byte cp.async copies (SASS LDGSTS):
-    // thread (r0, ch) = (tid / 20, tid % 20) copies chunk ch of rows r0, r0 + 6, ... (82 small
-    // bulk copies per CTA were measured slower: the TMA unit serialises them)
+    // thread (r0, ch) = (tid / 20, tid % 20) copies chunk ch of rows r0, r0 + 6, ...  (Bulk / TMA copies were
+    // measured slower twice: 82 row copies in round 1, and 40 row-PAIR copies of 640 bytes completing on one
+    // mbarrier in round 2 -- no LSU wavefronts for the load, yet 15.43 -> 15.86 ms: every bulk copy with per-lane
+    // operands costs a ~15-instruction serialisation loop, and the TMA unit queues them.)
     if (tid < 120) {
         const int r0 = tid / 20, ch = tid - r0 * 20;
         const double* sg_ = St + r0 * D + 2 * ch;
