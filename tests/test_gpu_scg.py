@@ -187,3 +187,36 @@ def test_simulation_run_with_device_optimizer(model, capsys):
     assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6
     assert abs(sim.output["fx"] - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0)
     assert {"at", "bt", "fx", "m0", "s0", "mt", "st", "Efx", "Edf", "lamt", "psit"} <= set(sim.output)
+
+
+def test_cache_is_not_fooled_by_in_place_mutation():
+    """The reference recomputes free_energy(x) on every call; the CUDA VarGP caches the last evaluation and must
+    therefore notice an x that was MUTATED IN PLACE between calls (coordinate-wise finite differences, sparse
+    updates), including at entries a strided probe would skip."""
+    from vgpa_b200 import Simulation
+    sim = Simulation("t")
+    sim.setup(mg.config("L63", "rk2", 20.0))                         # 24 024 parameters: the probe looks at every 11th
+    vgpa = sim.build()
+    x = vgpa.initialization()
+    assert vgpa._probe_step(x.size) > 1
+    f0 = vgpa.free_energy(x)
+    n0 = vgpa.n_eval
+    assert vgpa.free_energy(x) == f0 and vgpa.n_eval == n0          # same array, same content: cached
+    for pos in (1, x.size // 3 + 1, x.size - 1):                     # odd positions: off any power-of-two stride
+        old = x[pos]
+        x[pos] += 1e-3
+        f1 = vgpa.free_energy(x)
+        assert f1 != f0 and vgpa.n_eval > n0
+        n0 = vgpa.n_eval
+        x[pos] = old
+        assert vgpa.free_energy(x) == f0                             # and back: recomputed, same value
+        n0 = vgpa.n_eval
+    g = vgpa.gradient(x)
+    h = 1e-6
+    x[5] += h
+    fp = vgpa.free_energy(x)
+    x[5] -= 2 * h
+    fm = vgpa.free_energy(x)
+    x[5] += h
+    assert np.isfinite((fp - fm) / (2 * h)) and g.shape == x.shape
+    vgpa.close()

@@ -163,3 +163,38 @@ def test_simulation_save_and_load_schemas(tmp_path, monkeypatch):
     sim.save()
     assert calls[0] == ("open", "Sim_test.h5", "w")
     assert ("fx", (1,), "gzip") in calls and ("mt", (3, 2), "gzip") in calls and ("obs_t", (2,), "gzip") in calls
+
+
+def test_host_equal_and_copy_helpers():
+    """vgpa_host_equal / vgpa_host_copy (no device involved): the bytewise comparison behind VarGP's
+    "same x as the last evaluation" test, single- and multi-threaded, including a difference in the last
+    element of the last thread's part and signed zeros (bytewise, unlike ==)."""
+    from vgpa_b200._lib import lib
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 1000, (5 << 20) // 8 + 3):
+        a = rng.standard_normal(n)
+        b = np.empty_like(a)
+        lib.vgpa_host_copy(b.ctypes.data, a.ctypes.data, a.nbytes, 4)
+        assert np.array_equal(a, b)
+        for threads in (1, 4):
+            assert lib.vgpa_host_equal(a.ctypes.data, b.ctypes.data, a.nbytes, threads) == 1
+        if n:
+            for pos in (0, n // 2, n - 1):
+                c = b.copy()
+                c[pos] = np.nextafter(c[pos], np.inf)
+                assert lib.vgpa_host_equal(a.ctypes.data, c.ctypes.data, a.nbytes, 4) == 0
+    z = np.zeros(4)
+    mz = -np.zeros(4)
+    assert lib.vgpa_host_equal(z.ctypes.data, mz.ctypes.data, z.nbytes, 1) == 0
+
+
+def test_ensemble_writer_keys(tmp_path):
+    """save_ensemble: the reference's Simulation.save convention (one dataset per key, scalars as 1-D arrays)
+    with a leading problem axis; readable by vgpa_b200.simulation.load."""
+    from vgpa_b200.batched_scg import save_ensemble
+    from vgpa_b200.simulation import load
+    out = {"fx": np.arange(5.0), "n_it": np.arange(5), "at": np.zeros((2, 7, 3, 3)), "bt": np.ones((2, 7, 3)), "seed": 3}
+    path = save_ensemble(str(tmp_path / "ens"), out)
+    z = load(path)
+    assert set(z) == set(out) and z["seed"].shape == (1,) and z["at"].shape == (2, 7, 3, 3)
+    assert np.array_equal(z["fx"], out["fx"])
