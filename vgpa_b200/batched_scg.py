@@ -333,12 +333,13 @@ class ShardedBatchedSCG:
         self.sub_batch, self.mem_fraction = sub_batch, mem_fraction
         self.result = None
 
-    def _pick_sub_batch(self, n_x, device, scratch_bytes):
+    def _pick_sub_batch(self, n_x, device, scratch_per_problem):
+        """Problems resident at once: the optimiser's five (B, n) buffers plus the evaluator's scratch (which
+        holds the trajectories of up to one pass = up to the whole sub-batch) within `mem_fraction` of the free HBM."""
         import torch
         free, _ = torch.cuda.mem_get_info(device)
-        per_problem = 5 * 8 * n_x + 64
-        fit = int((free * self.mem_fraction - scratch_bytes) // per_problem)
-        return max(1, fit)
+        per_problem = 5 * 8 * n_x + scratch_per_problem + 64
+        return max(1, int(free * self.mem_fraction // per_problem))
 
     def run(self, t0=0.0, x0_fn=None, keep=()):
         """Optimise the local block.  x0_fn(lo, hi, X) fills the (hi - lo, n) device tensor X with starting
@@ -362,8 +363,8 @@ class ShardedBatchedSCG:
             if sub is None:       # decide once, from the first (largest possible) evaluator's shape
                 ev.close()
                 dev = torch.device("cuda", ev.device)
-                # evaluator scratch: 2 (D + D^2) N + N doubles per resident problem, one chunk of at most 888
-                scratch = 8 * ev.N * (2 * ev.D * (ev.D + 1) + 1) * 888
+                # evaluator scratch: 2 (D + D^2) N + N doubles per problem of a pass
+                scratch = 8 * ev.N * (2 * ev.D * (ev.D + 1) + 1)
                 sub = min(self.hi - self.lo, self._pick_sub_batch(ev.n_x, dev, scratch))
                 continue
             b = ev.B
