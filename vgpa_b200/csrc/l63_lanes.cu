@@ -186,17 +186,28 @@ __device__ __forceinline__ void mid_aops(AOps& o, const AOps& lo, const AOps& hi
         o.V2[k] = 0.5 * (lo.V2[k] + hi.V2[k]);
     }
 }
-__device__ __forceinline__ double bwd_fun(double Y, const AOps& a, double G, int i, int j)
+// row i of Psi (lanes of the vector column: lam) as every lane needs it for the left products
+__device__ __forceinline__ void row_of(double Y, int i, int j, double (&ya)[3])
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ya[k] = shfl16(Y, (j < 3) ? 4 * i + k : 4 * k + 3);   // Psi_ik, or lam_k
+}
+__device__ __forceinline__ double bwd_fun(const double (&ya)[3], double Y, const AOps& a, double G, int j)
 {
     double p = 0.0, q = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double ya = shfl16(Y, (j < 3) ? 4 * i + k : 4 * k + 3);   // Psi_ik, or lam_k for the vector column
         const double yb = shfl16(Y, 4 * k + j);                         // Psi_kj
-        p += ya * a.V1[k];
+        p += ya[k] * a.V1[k];
         q += a.V2[k] * yb;
     }
     return (j < 3) ? (-G + p + q) : (-G + p);
+}
+__device__ __forceinline__ double bwd_fun(double Y, const AOps& a, double G, int i, int j)
+{
+    double ya[3];
+    row_of(Y, i, j, ya);
+    return bwd_fun(ya, Y, a, G, j);
 }
 
 // shared memory of one warp: [buffer][group][A | S | dE/dS : NI x 9 each | b | m | dE/dm : NI x 3 each];
@@ -265,8 +276,23 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
         const double* sm = sb + NI * D;
         const double* sg = sb + 2 * NI * D;
         const int tend = max(top - TB + 1, 0);
+        // operands of A and my entry of dE/dS (dE/dm) at index t: loaded at the top of a block, then handed down
+        // from step to step (index t - 1 of one step is index t of the next)
+        AOps at;
+        double Gt;
+        {
+            const int u0 = top - lo;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                at.V1[k] = sA[u0 * DD + ((j < 3) ? 3 * k + j : 3 * i + k)];
+                at.V2[k] = sA[u0 * DD + 3 * k + i];
+            }
+            Gt = (j < 3) ? sG[u0 * DD + 3 * i + j] : sg[u0 * D + i];
+        }
         for (int t = top; t >= tend; --t) {
             const int u = t - lo, up = (t >= 1) ? u - 1 : u;           // slots of index t and t - 1
+            double ya[3];
+            row_of(Y, i, j, ya);                                       // shared by the gradient and the first stage
             // ---- gradient at index t (variational.py:280-334; grad_at of small_dim.cu) ----
             {
                 double Ar[3], m[3], Sc[3];
@@ -278,12 +304,9 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
                 }
                 const double Sx = sS[u * DD + sx], bt = sb[u * D + i];
                 const double lam_i = shfl16(Y, 4 * i + 3);
-                double Pr[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) Pr[k] = shfl16(Y, 4 * i + k);        // row i of Psi
                 const L63Row r = l63_row_terms(i, vS, vR, vB, m, Sx, Ar, bt, isg_i);
                 const double mj = (j == 1) ? m[1] : (j == 2 ? m[2] : m[0]);      // (selects: no dynamic register indexing)
-                const double ga = l63_grad_a(r, Sc, Pr, mj, lam_i, dtm);
+                const double ga = l63_grad_a(r, Sc, ya, mj, lam_i, dtm);          // (ya = row i of Psi for the matrix lanes)
                 const double gbv = l63_grad_b(r, lam_i, dtm);
                 if (on) gdst[(long long)t * gstride] = (j < 3) ? ga : gbv;
             }
@@ -297,24 +320,20 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
                     jsv = 0.5 / Rv_i;
                 }
             }
-            // operands of A and my entry of dE/dS (dE/dm) at index t and t - 1
-            AOps at, am1;
+            // ... and at index t - 1
+            AOps am1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const int o1_ = (j < 3) ? 3 * k + j : 3 * i + k;
-                at.V1[k] = sA[u * DD + o1_];
-                at.V2[k] = sA[u * DD + 3 * k + i];
-                am1.V1[k] = sA[up * DD + o1_];
+                am1.V1[k] = sA[up * DD + ((j < 3) ? 3 * k + j : 3 * i + k)];
                 am1.V2[k] = sA[up * DD + 3 * k + i];
             }
-            const double Gt = (j < 3) ? sG[u * DD + 3 * i + j] : sg[u * D + i];
             const double Gm = (j < 3) ? sG[up * DD + 3 * i + j] : sg[up * D + i];
             double Yn;
             if (METHOD == ODE_EULER) {                  // euler.py:146-149
-                const double o1 = bwd_fun(Y, at, Gt, i, j);
+                const double o1 = bwd_fun(ya, Y, at, Gt, j);
                 Yn = (j < 3) ? (Y - o1 * dt) : (Y - o1 * dt + jmv);
             } else if (METHOD == ODE_HEUN) {            // heun.py:170-185
-                const double o1 = bwd_fun(Y, at, Gt, i, j);
+                const double o1 = bwd_fun(ya, Y, at, Gt, j);
                 const double tmp = Y + (-dt) * o1;
                 const double o2 = bwd_fun(tmp, am1, Gm, i, j);
                 Yn = (j < 3) ? (Y - h * (o1 + o2)) : (Y - h * (o1 + o2) + jmv);
@@ -322,7 +341,7 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
                 AOps amid;
                 mid_aops(amid, am1, at);
                 const double Gmid = 0.5 * (Gm + Gt);
-                const double o1 = bwd_fun(Y, at, Gt, i, j);
+                const double o1 = bwd_fun(ya, Y, at, Gt, j);
                 const double tmp = Y + (-h) * o1;
                 const double o2 = bwd_fun(tmp, amid, Gmid, i, j);
                 Yn = (j < 3) ? (Y - dt * o2) : (Y - dt * o2 + jmv);
@@ -330,7 +349,7 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
                 AOps amid;
                 mid_aops(amid, am1, at);
                 const double Gmid = 0.5 * (Gm + Gt);
-                const double o1 = bwd_fun(Y, at, Gt, i, j);
+                const double o1 = bwd_fun(ya, Y, at, Gt, j);
                 double tmp = Y + (-h) * o1;
                 const double o2 = bwd_fun(tmp, amid, Gmid, i, j);
                 tmp = Y + (-h) * o2;
@@ -342,6 +361,8 @@ l63_bwd_lanes_kernel(Batch b, Scratch s, const double* __restrict__ x, long long
             }
             if (i == j) Yn += jsv;
             Y = Yn;
+            at = am1;
+            Gt = Gm;
         }
         __syncwarp();                                                 // the buffer is refilled by the next issue
     }
