@@ -63,6 +63,8 @@ struct vgpa_handle {
     DevBuf plist2[2];                   // vgpa_set_active_list: compacted list of problem indices (device copies,
     int plist_flip = 0;                 //   alternating: the evaluation in flight may still read the previous one)
     cudaStream_t s_aux = nullptr;       //   non-blocking stream of the list upload
+    cudaEvent_t plist_ev[2] = {nullptr, nullptr};   //   end of the last evaluation that read each copy
+    bool plist_used[2] = {false, false};
     std::vector<int> plist_host;        // ... and the host copy (error messages name the problem, not the position)
     int n_list = -1;                    // < 0: no list, every problem
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -396,6 +398,8 @@ void vgpa_destroy(vgpa_handle* h)
                       &h->st_x[1], &h->st_g[0], &h->st_g[1], &h->st_F, &h->plist2[0], &h->plist2[1]})
         b->release();
     if (h->s_aux) cudaStreamDestroy(h->s_aux);
+    for (int q = 0; q < 2; ++q)
+        if (h->plist_ev[q]) cudaEventDestroy(h->plist_ev[q]);
     for (int q = 0; q < 2; ++q) {
         if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
         if (h->ev_comp[q]) cudaEventDestroy(h->ev_comp[q]);
@@ -453,6 +457,12 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
         }
     }
     CK(cudaGetLastError(), "kernel launch");
+    if (h->batch.plist != nullptr && h->n_list >= 0) {   // this evaluation reads the current copy of the list
+        const int q = h->plist_flip;
+        if (h->plist_ev[q] == nullptr) CK(cudaEventCreateWithFlags(&h->plist_ev[q], cudaEventDisableTiming), "cudaEventCreate");
+        CK(cudaEventRecord(h->plist_ev[q], st), "cudaEventRecord");
+        h->plist_used[q] = true;
+    }
     h->last_stream = st;
     h->status_dirty = true;
     return VGPA_OK;
@@ -486,6 +496,10 @@ int vgpa_set_active_list(vgpa_handle* h, const int32_t* list, int32_t n)
     // waits for its own tiny copy only, never for the kernels already enqueued on the caller's stream.
     h->plist_flip ^= 1;
     DevBuf& buf = h->plist2[h->plist_flip];
+    if (h->plist_used[h->plist_flip]) {    // an evaluation two list changes ago read this copy: it must be over
+        CK(cudaEventSynchronize(h->plist_ev[h->plist_flip]), "cudaEventSynchronize");
+        h->plist_used[h->plist_flip] = false;
+    }
     const size_t bytes = sizeof(int) * (size_t)std::max(h->d.B, 1);
     if (buf.bytes < bytes) CK(buf.alloc(bytes), "cudaMalloc(list)");
     if (h->s_aux == nullptr) CK(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking), "cudaStreamCreate");
