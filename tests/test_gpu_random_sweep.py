@@ -1,0 +1,78 @@
+"""
+Randomised sweep of the CUDA path against the oracle (through the C ABI): for every model and solver,
+several draws of the grid length, the batch size (odd and even: the Lorenz-63 kernels pack two problems
+per warp), the observation set (count, positions -- including index 0 and the last index --, values), the
+noises and the evaluation points; every problem of every batch is held to the oracle at 1e-9 (F, and the
+gradient per block), and a masked re-evaluation (vgpa_set_active) must leave the masked rows untouched.
+Seeds are fixed: the sweep is a regression net, not a fuzzer.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_eval_files, grad_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _load(name):
+    return np.load(str(next(p for p in golden_eval_files() if name in p)))
+
+
+@pytest.mark.parametrize("model", ["DW", "OU", "L63", "L96"])
+@pytest.mark.parametrize("method", ["euler", "heun", "rk2", "rk4"])
+def test_random_configurations_match_oracle(oracle, model, method):
+    import torch
+    from oracle import Problem, prior_kl0
+    from vgpa_b200.engine import BatchEvaluator
+    g = _load(f"eval_{model}_{method}")
+    D, N0 = int(g["D"]), int(g["N"])
+    rng = np.random.default_rng([17, D, {"euler": 0, "heun": 1, "rk2": 2, "rk4": 3}[method]])
+    n_draws = 2 if model == "L96" else 4
+    for draw in range(n_draws):
+        N = int(rng.integers(2, N0 + 1)) if model != "L96" else int(rng.integers(3, N0 + 1))
+        B = int(rng.integers(1, 8))
+        M = int(rng.integers(0, min(6, N) + 1))
+        obs_t = np.sort(rng.choice(N, size=M, replace=False)).astype(np.int64)
+        if M >= 2 and draw % 2 == 0:
+            obs_t[0], obs_t[-1] = 0, N - 1                      # both ends of the grid
+            obs_t = np.unique(obs_t)
+            M = obs_t.size
+        scale = float(np.abs(g["obs_y"]).max()) if g["obs_y"].size else 1.0
+        obs_y = scale * 0.5 * rng.standard_normal((B, M, D))
+        sigma = np.stack([g["sigma"] * rng.uniform(0.6, 1.5) for _ in range(B)])
+        R = np.stack([g["R"] * rng.uniform(0.6, 1.5) for _ in range(B)])
+        theta = np.stack([g["theta"] * rng.uniform(0.95, 1.05) for _ in range(B)])
+        m0 = np.stack([g["m0"] + 0.05 * rng.standard_normal(D) for _ in range(B)])
+        s0 = np.stack([g["s0"] * rng.uniform(0.8, 1.3) for _ in range(B)])
+        E0 = np.array([prior_kl0(m0[i], s0[i].reshape(D, D) if D > 1 else s0[i], g["mu0"], g["tau0"], D == 1)
+                       for i in range(B)])
+        # the first N time points of the golden evaluation point, jittered per problem
+        x = g["x"]
+        xN = np.concatenate([x[:N0 * D * D].reshape(N0, -1)[:N].ravel(), x[N0 * D * D:].reshape(N0, -1)[:N].ravel()])
+        X = np.stack([xN * (1.0 + 0.01 * rng.standard_normal(xN.size)) for _ in range(B)])
+        dt = float(g["dt"])
+        with BatchEvaluator(model, method, N, dt, theta, sigma, R, obs_t, obs_y, m0, s0, E0, B=B, dt_model=dt) as ev:
+            F, G = ev.eval(X)
+            # masked device evaluation: rows whose flag is 0 keep their sentinel values
+            Xd = torch.from_numpy(X).cuda()
+            Fd = torch.full((B,), -7.0, dtype=torch.float64, device="cuda")
+            Gd = torch.full_like(Xd, -7.0)
+            keep = rng.integers(0, 2, size=B).astype(np.int32)
+            mask = torch.from_numpy(keep).cuda()
+            ev.set_active(mask.data_ptr())
+            ev.eval_device(Xd.data_ptr(), ev.n_x, Fd.data_ptr(), Gd.data_ptr(), ev.n_x, torch.cuda.current_stream().cuda_stream)
+            ev.sync()
+            ev.set_active(None)
+            Fm, Gm = Fd.cpu().numpy(), Gd.cpu().numpy()
+        for i in range(B):
+            prob = Problem(model=model, method=method, D=D, N=N, dt=dt, theta=theta[i], sigma=sigma[i], R=R[i],
+                           obs_t=obs_t, obs_y=obs_y[i], m0=m0[i], s0=s0[i], E0=float(E0[i]), dt_model=dt)
+            Fo, Go = oracle.eval(prob, X[i])
+            tag = (model, method, draw, N, B, M, i)
+            assert abs(F[i] - Fo) <= TOL * abs(Fo), tag
+            assert grad_err(G[i], Go, N, D) < TOL, tag
+            if keep[i]:
+                assert Fm[i] == F[i] and np.array_equal(Gm[i], G[i]), tag
+            else:
+                assert Fm[i] == -7.0 and np.all(Gm[i] == -7.0), tag
