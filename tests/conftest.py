@@ -50,3 +50,13 @@ def key_err(key, got, ref, N, D):
 def oracle():
     from oracle import Oracle
     return Oracle()
+
+
+def stop_tolerance(trace_fx, n_ref):
+    """How far an SCG run's stopping iteration may be from the reference's.  A few iterations either way
+    because of the |f_new - f_old| <= 1e-8 test -- and where the reference's trace ends in a plateau (OU: fx
+    unchanged TO THE LAST BIT over the final iterations, SCG only raising lambda until the step falls under
+    x_tol) the exit is decided by rounding: allow a quarter of the plateau, at most 5 iterations."""
+    tr = np.asarray(trace_fx, dtype=float)
+    plateau = int(np.argmax(np.abs(tr[::-1] - tr[-1]) > 1e-13 * max(abs(tr[-1]), 1.0)))
+    return max(2, n_ref // 50, min(plateau // 4, 5))

@@ -61,7 +61,7 @@ def test_batched_scg_matches_reference_scg_trace(model):
     the fx / beta traces recorded by the unmodified reference's own SCG + VarGP,
     src/numerics/optim_scg.py:75-285), optimised on the device as a batch of three copies -- every
     row must follow the reference trace within 1e-6 on the common prefix (BASELINE.json)."""
-    from conftest import GOLDEN
+    from conftest import GOLDEN, stop_tolerance
     from test_gpu_parity import evaluator_from_golden
     from vgpa_b200.batched_scg import BatchedSCG
     g = np.load(GOLDEN / f"scg_{model}.npz")
@@ -75,7 +75,7 @@ def test_batched_scg_matches_reference_scg_trace(model):
     for p in range(B):
         n_new = int(st["MaxIt"][p])
         n = min(n_ref, n_new)
-        assert abs(n_ref - n_new) <= max(2, n_ref // 50), (p, n_ref, n_new)
+        assert abs(n_ref - n_new) <= stop_tolerance(g["trace_fx"], n_ref), (p, n_ref, n_new)
         ref, new = g["trace_fx"][:n], st["fx"][:n, p]
         assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6, p
         assert abs(fx[p] - float(g["fx_final"])) <= 1e-6 * max(abs(float(g["fx_final"])), 1.0), p

@@ -140,10 +140,11 @@ def test_small_models_at_full_size_match_oracle(oracle, model, method, N):
 @pytest.mark.parametrize("model,method,N", [("L63", "rk2", 61), ("L63", "rk4", 30), ("OU", "rk4", 75),
                                             ("DW", "euler", 40), ("OU", "heun", 18)])
 def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
-    """Batches above 8192 problems run the staged forward sweep (small_dim.cu: blocks of time indices
-    through shared memory).  Its arithmetic is the per-thread kernel's, so a problem's result must be
-    bitwise the same in a 8 500-problem batch (staged; ragged last warp, ragged last block) and in a
-    small batch (register-prefetch kernel); sampled rows are also held to the oracle."""
+    """Batches above 8192 (L63) / 16384 (D = 1) problems run the staged forward sweep (small_dim.cu: blocks of time indices
+    through shared memory) and the one-thread-per-problem backward sweep; small batches run the lane-parallel
+    (L63) or time-parallel (D = 1) kernels.  A problem's result in such a batch (ragged last warp,
+    ragged last block) must agree with its result in a small batch to rounding, be bitwise independent of
+    its position inside either, and sampled rows are held to the oracle."""
     from vgpa_b200.engine import BatchEvaluator
     D = 3 if model == "L63" else 1
     rng = np.random.default_rng(23)
@@ -152,7 +153,7 @@ def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
     theta = [10.0, 28.0, 2.6667] if model == "L63" else ([2.0] if model == "OU" else [1.0])
     sig = np.full(D, 10.0 if model == "L63" else 0.8)
     R = np.full(D, 2.0 if model == "L63" else 0.04)
-    B = 8500
+    B = 8500 if model == "L63" else 17000          # above the small-batch kernels' limits (8192 / 16384)
     obs_y = rng.standard_normal((B, M, D)) * (3.0 if model == "L63" else 0.5)
     m0 = rng.standard_normal((B, D))
     s0 = 0.25 * np.eye(D)
@@ -165,21 +166,24 @@ def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
     with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows], m0[rows], s0,
                         np.zeros(rows.size), B=rows.size) as ev:
         Fs, Gs = ev.eval(X[rows])
-    assert np.array_equal(F[rows], Fs)
     if model == "L63":
         # small Lorenz-63 batches run the lane-parallel kernels (l63_lanes.cu), large ones the one-thread-per-
         # problem kernels: the same operations in the same order, F bit for bit, but the compiler contracts a few
         # products differently around the lane-dependent control flow -- last-bit differences in isolated
         # gradient entries (observed: <= 2e-16 of the largest entry)
+        assert np.array_equal(F[rows], Fs)
         assert np.abs(G[rows] - Gs).max() <= 1e-13 * np.abs(Gs).max()
-        # ... while inside one kernel family a problem's result does not depend on its position or neighbours
-        rows2 = rows[::-1].copy()
-        with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows2], m0[rows2], s0,
-                            np.zeros(rows2.size), B=rows2.size) as ev:
-            F2, G2 = ev.eval(X[rows2])
-        assert np.array_equal(F2[::-1], Fs) and np.array_equal(G2[::-1], Gs)
     else:
-        assert np.array_equal(G[rows], Gs)
+        # small D = 1 batches run the time-parallel sweeps (small_dim.cu, scan1_*): each lane's run of steps
+        # starts from a state composed by a scan, so results differ from the sequential kernels by rounding
+        assert np.abs(F[rows] - Fs).max() <= 1e-12 * np.abs(Fs).max()
+        assert np.abs(G[rows] - Gs).max() <= 1e-11 * np.abs(Gs).max()
+    # inside one kernel family a problem's result does not depend on its position or on its neighbours
+    rows2 = rows[::-1].copy()
+    with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows2], m0[rows2], s0,
+                        np.zeros(rows2.size), B=rows2.size) as ev:
+        F2, G2 = ev.eval(X[rows2])
+    assert np.array_equal(F2[::-1], Fs) and np.array_equal(G2[::-1], Gs)
     for r in (0, 31, 4242, B - 1):
         prob = Problem(model=model, method=method, D=D, N=N, dt=0.01, theta=theta, sigma=sig, R=R, obs_t=obs_t,
                        obs_y=obs_y[r], m0=m0[r], s0=s0, E0=0.0)

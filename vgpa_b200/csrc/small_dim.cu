@@ -833,6 +833,186 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
 }
 
 // ---------------------------------------------------------------------------
+// D = 1 (DW, OU), small batches: time-parallel sweeps, one 128-thread CTA per problem.
+//
+// With one thread per problem the sweeps above are a chain of N-1 dependent solver steps (~450 cycles
+// each: OU x 1024, N = 1001 took 0.26 + 0.61 ms whatever the batch size).  But both moment ODEs are
+// LINEAR in their state -- m' = -A m + b, S' = -2 A S + sigma, lam' and Psi' likewise
+// (fwd_ode.py:41-75, bwd_ode.py:45-83) -- so one solver step is an affine map y -> P y + Q of each scalar,
+// whatever the solver (the one exception: RK2's forward variance stage, runge_kutta2.py:92, passes S in
+// place of A and is quadratic in S; that sweep stays sequential).  The CTA first stages the problem's
+// streams (A, b; backward also m, S, dE/dm, dE/dS) in shared memory with coalesced loads; then each thread
+// takes a contiguous run of ~(N-1)/128 steps and
+//   1. finds the (P, Q) of every step of its run by applying THE SOLVER STEP ITSELF (fwd_step / bwd_step,
+//      observation jumps included) to the states 0 and 1, and composes them;
+//   2. a block scan composes the runs, giving each thread the state at the start of its run;
+//   3. the thread walks its run again from that state with the solver step, storing m(t), S(t) (forward)
+//      or assembling dL/dA(t), dL/db(t) (backward) exactly as the sequential kernels do.
+// The chain is ~2 x 8 steps + the scan instead of 1000 steps, for ~3x the arithmetic.  Only the run-start
+// states differ from the sequential kernels (rounding of the composed maps, ~1e-16 relative per step);
+// inside a run the arithmetic is the sequential one.
+// ---------------------------------------------------------------------------
+constexpr int SCAN_MAX_BATCH = 16384;     // above: one thread per problem fills the FP64 pipe better (measured, OU rk4:
+                                          // 12.4 M evaluations/s time-parallel at 8192 problems, 14.5 M/s sequential at 65536)
+constexpr int SCAN_THREADS = 128;
+constexpr size_t SCAN_MAX_SMEM = 200 * 1024;
+
+struct Affine { double P, Q; };           // y -> P y + Q
+__device__ __forceinline__ Affine after(const Affine& later, const Affine& earlier)
+{
+    return {later.P * earlier.P, fma(later.P, earlier.Q, later.Q)};
+}
+// composition of the maps of threads 0 .. tid-1 (thread 0 first); identity for thread 0.
+// sh: SCAN_THREADS / 32 slots.  Contains block barriers.
+__device__ __forceinline__ Affine scan_exclusive(Affine f, Affine* sh)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Affine o{__shfl_up_sync(0xffffffffu, f.P, d), __shfl_up_sync(0xffffffffu, f.Q, d)};
+        if (lane >= d) f = after(f, o);
+    }
+    if (lane == 31) sh[w] = f;
+    Affine e{__shfl_up_sync(0xffffffffu, f.P, 1), __shfl_up_sync(0xffffffffu, f.Q, 1)};
+    if (lane == 0) e = {1.0, 0.0};
+    __syncthreads();
+    Affine pre{1.0, 0.0};
+    for (int q = 0; q < w; ++q) pre = after(sh[q], pre);
+    __syncthreads();
+    return after(e, pre);
+}
+__device__ __forceinline__ void stage_array(double* __restrict__ dst, const double* __restrict__ src, int n)
+{
+    for (int i = threadIdx.x; i < n; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count)
+{
+    static_assert(METHOD != ODE_RK2, "RK2's forward variance stage is quadratic in S");
+    extern __shared__ double scan_sm[];
+    __shared__ Affine sh[2][SCAN_THREADS / 32];
+    const int lp = blockIdx.x, tid = threadIdx.x;
+    const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    double* A = scan_sm;
+    double* bo = A + N;
+    stage_array(A, x + (long long)p * xs, 2 * N);          // A then b, contiguous in x
+    const double sig = b.sigma[p * b.sigma_stride], dt = b.dt;
+    const double m0 = b.m0[p * b.m0_stride], S0 = b.s0[p * b.s0_stride];
+    double* mt = s.mt + (long long)lp * N;
+    double* st = s.st + (long long)lp * N;
+    const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int k0 = min(tid * L, steps), k1 = min(k0 + L, steps);
+    const double zero = 0.0, one = 1.0;
+    __syncthreads();
+    Affine fm{1.0, 0.0}, fS{1.0, 0.0};
+    for (int k = k0; k < k1; ++k) {
+        double qm, qS, rm, rS;
+        fwd_step<1, METHOD>(&zero, &zero, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &qm, &qS);
+        fwd_step<1, METHOD>(&one, &one, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &rm, &rS);
+        fm = after(Affine{rm - qm, qm}, fm);
+        fS = after(Affine{rS - qS, qS}, fS);
+    }
+    const Affine em = scan_exclusive(fm, sh[0]), eS = scan_exclusive(fS, sh[1]);
+    double m = (tid == 0) ? m0 : fma(em.P, m0, em.Q);
+    double S = (tid == 0) ? S0 : fma(eS.P, S0, eS.Q);
+    if (tid == 0) {
+        mt[0] = m0;
+        st[0] = S0;
+    }
+    for (int k = k0; k < k1; ++k) {
+        double mn, Sn;
+        fwd_step<1, METHOD>(&m, &S, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &mn, &Sn);
+        mt[k + 1] = mn;
+        st[k + 1] = Sn;
+        m = mn;
+        S = Sn;
+    }
+}
+
+template <int MODEL, int METHOD>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count)
+{
+    extern __shared__ double scan_sm[];
+    __shared__ Affine sh[2][SCAN_THREADS / 32];
+    const int lp = blockIdx.x, tid = threadIdx.x;
+    const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    double* A = scan_sm;
+    double* bo = A + N;
+    double* mt = bo + N;
+    double* st = mt + N;
+    double* dEm = st + N;
+    double* dEs = dEm + N;
+    stage_array(A, a.x + (long long)p * a.xs, 2 * N);
+    stage_array(mt, s.mt + (long long)lp * N, N);
+    stage_array(st, s.st + (long long)lp * N, N);
+    stage_array(dEm, s.dEm + (long long)lp * N, N);
+    stage_array(dEs, s.dEs + (long long)lp * N, N);
+    double* gA = a.grad + (long long)p * a.gs;
+    double* gb = gA + N;
+    const double* th = b.theta + p * b.theta_stride;
+    const double* oy = b.obs_y + p * b.obs_y_stride;
+    const double isg = 1.0 / b.sigma[p * b.sigma_stride], Rv = b.R[p * b.R_stride];
+    const double dt = b.dt, dtm = b.dt_model;
+    // step q = 0 .. N-2 takes index t = N-1-q to t-1
+    const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int q0 = min(tid * L, steps), q1 = min(q0 + L, steps);
+    const double zero = 0.0, one = 1.0;
+    __syncthreads();
+
+    // jump of lambda and Psi at index t (gaussian_like.py:188,191), as in small_bwd_kernel
+    auto jump = [&](int t, double& jm, double& js) {
+        const int n = b.obs_index[t];
+        jm = 0.0;
+        js = 0.0;
+        if (n >= 0) {
+            jm = -(oy[n] - mt[t]) / Rv;
+            js = 0.5 / Rv;
+        }
+    };
+    Affine fl{1.0, 0.0}, fP{1.0, 0.0};
+    for (int q = q0; q < q1; ++q) {
+        const int t = N - 1 - q;
+        double jm, js, ql, qP, rl, rP;
+        jump(t - 1, jm, js);
+        bwd_step<1, METHOD>(&zero, &zero, A + t, dEm + t, dEs + t, A + t - 1, dEm + t - 1, dEs + t - 1, &jm, dt, &ql, &qP);
+        bwd_step<1, METHOD>(&one, &one, A + t, dEm + t, dEs + t, A + t - 1, dEm + t - 1, dEs + t - 1, &jm, dt, &rl, &rP);
+        qP += js;
+        rP += js;
+        fl = after(Affine{rl - ql, ql}, fl);
+        fP = after(Affine{rP - qP, qP}, fP);
+    }
+    const Affine el = scan_exclusive(fl, sh[0]), eP = scan_exclusive(fP, sh[1]);
+    double lam = (tid == 0) ? 0.0 : el.Q;      // the terminal state is zero: P * 0 + Q
+    double Psi = (tid == 0) ? 0.0 : eP.Q;
+    auto grad = [&](int t) {
+        double ga, gbv;
+        grad_at<MODEL, 1>(th, &isg, dtm, A + t, bo + t, mt + t, st + t, &lam, &Psi, &ga, &gbv);
+        gA[t] = ga;
+        gb[t] = gbv;
+    };
+    for (int q = q0; q < q1; ++q) {
+        const int t = N - 1 - q;
+        grad(t);
+        double jm, js, ln, Pn;
+        jump(t - 1, jm, js);
+        bwd_step<1, METHOD>(&lam, &Psi, A + t, dEm + t, dEs + t, A + t - 1, dEm + t - 1, dEs + t - 1, &jm, dt, &ln, &Pn);
+        lam = ln;
+        Psi = Pn + js;
+    }
+    // index 0: the thread that took the last step (thread 0 when the grid has a single point)
+    if ((steps == 0) ? (tid == 0) : (q0 < q1 && q1 == steps)) grad(0);
+}
+// shared memory of the two kernels for a grid of N points; the launchers fall back to the sequential
+// kernels when it does not fit
+static inline size_t scan_fwd_bytes(int N) { return sizeof(double) * 2 * (size_t)N; }
+static inline size_t scan_bwd_bytes(int N) { return sizeof(double) * 6 * (size_t)N; }
+
+// ---------------------------------------------------------------------------
 // F = E0 + Esde + Eobs : one CTA per problem, fixed-order reductions (bitwise
 // reproducible, so a sharded batch returns the same F as a single-GPU one).
 // ---------------------------------------------------------------------------
@@ -911,6 +1091,23 @@ template <int D>
 static void fwd_dispatch(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
                          int count, cudaStream_t st)
 {
+    if constexpr (D == 1) {
+        const size_t sh = scan_fwd_bytes(b.N);
+        if (count <= SCAN_MAX_BATCH && b.method != ODE_RK2 && sh <= SCAN_MAX_SMEM) {   // time-parallel
+#define VGPA_SCAN_FWD(M)                                                                                  \
+    do {                                                                                                  \
+        cudaFuncSetAttribute(scan1_fwd_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);  \
+        scan1_fwd_kernel<M><<<count, SCAN_THREADS, sh, st>>>(b, s, x, xs, p0, count);                     \
+    } while (0)
+            switch (b.method) {
+            case ODE_EULER: VGPA_SCAN_FWD(ODE_EULER); break;
+            case ODE_HEUN:  VGPA_SCAN_FWD(ODE_HEUN); break;
+            default:        VGPA_SCAN_FWD(ODE_RK4); break;
+            }
+#undef VGPA_SCAN_FWD
+            return;
+        }
+    }
     if (count > PF_MAX_BATCH) {   // large batches: streams staged through shared memory, one warp per CTA
         constexpr int TB = (D == 1) ? 16 : 8;
         const size_t sh = fwd_stage_bytes<D, TB>();
@@ -961,6 +1158,25 @@ template <int MODEL, int D>
 static void bwd_dispatch(const Batch& b, const Scratch& s, const SmallBwdArgs& a, int p0, int count,
                          const Extra& ex, cudaStream_t st)
 {
+    if constexpr (D == 1) {
+        const size_t sh = scan_bwd_bytes(b.N);
+        if (a.grad != nullptr && a.jm_dense == nullptr && ex.lamt == nullptr && count <= SCAN_MAX_BATCH &&
+            sh <= SCAN_MAX_SMEM) {   // time-parallel
+#define VGPA_SCAN_BWD(M)                                                                                        \
+    do {                                                                                                        \
+        cudaFuncSetAttribute(scan1_bwd_kernel<MODEL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+        scan1_bwd_kernel<MODEL, M><<<count, SCAN_THREADS, sh, st>>>(b, s, a, p0, count);                        \
+    } while (0)
+            switch (b.method) {
+            case ODE_EULER: VGPA_SCAN_BWD(ODE_EULER); break;
+            case ODE_HEUN:  VGPA_SCAN_BWD(ODE_HEUN); break;
+            case ODE_RK2:   VGPA_SCAN_BWD(ODE_RK2); break;
+            default:        VGPA_SCAN_BWD(ODE_RK4); break;
+            }
+#undef VGPA_SCAN_BWD
+            return;
+        }
+    }
     const int th = (count <= 148 * 64) ? 32 : 64, bl = (count + th - 1) / th;
     switch (b.method) {
     case ODE_EULER: small_bwd_kernel<MODEL, D, ODE_EULER><<<bl, th, 0, st>>>(b, s, a, p0, count, ex); break;
