@@ -76,3 +76,37 @@ def test_random_configurations_match_oracle(oracle, model, method):
                 assert Fm[i] == F[i] and np.array_equal(Gm[i], G[i]), tag
             else:
                 assert Fm[i] == -7.0 and np.all(Gm[i] == -7.0), tag
+
+
+@pytest.mark.parametrize("model", ["DW", "OU"])
+@pytest.mark.parametrize("method", ["euler", "heun", "rk2", "rk4"])
+def test_time_parallel_sweeps_at_run_boundaries(oracle, model, method):
+    """The D = 1 time-parallel sweeps (small_dim.cu, scan1_*) cut the N-1 steps into 128 runs: grid lengths
+    with fewer steps than threads (2, 3, 100), exactly one step per thread and one more (129, 130), ragged
+    last runs (300, 1538), and a grid too long for shared memory (4300: the sequential kernels), each with
+    observations on both ends of the grid and on neighbouring indices, against the oracle."""
+    from oracle import Problem
+    from vgpa_b200.engine import BatchEvaluator
+    rng = np.random.default_rng([23, {"euler": 0, "heun": 1, "rk2": 2, "rk4": 3}[method], model == "OU"])
+    theta = np.array([2.0] if model == "OU" else [1.0])
+    B = 3
+    for N in (2, 3, 100, 129, 130, 300, 1538, 4300):
+        M = min(N, 12)
+        obs_t = np.unique(np.concatenate([[0, N - 1], [N // 2, min(N // 2 + 1, N - 1)],
+                                          rng.choice(N, size=M, replace=False)])).astype(np.int64)
+        M = obs_t.size
+        obs_y = 0.7 * rng.standard_normal((B, M, 1))
+        sigma = rng.uniform(0.5, 1.2, size=(B, 1))
+        R = rng.uniform(0.03, 0.08, size=(B, 1))
+        m0 = rng.standard_normal((B, 1))
+        s0 = rng.uniform(0.2, 0.4, size=(B, 1, 1))
+        E0 = rng.standard_normal(B)
+        X = np.concatenate([1.6 + 0.2 * rng.standard_normal((B, N)), 0.3 * rng.standard_normal((B, N))], axis=1)
+        with BatchEvaluator(model, method, N, 0.01, theta, sigma, R, obs_t, obs_y, m0, s0, E0, B=B) as ev:
+            F, G = ev.eval(X)
+        for i in range(B):
+            prob = Problem(model=model, method=method, D=1, N=N, dt=0.01, theta=theta, sigma=sigma[i], R=R[i],
+                           obs_t=obs_t, obs_y=obs_y[i], m0=m0[i], s0=s0[i], E0=float(E0[i]))
+            Fo, Go = oracle.eval(prob, X[i])
+            assert abs(F[i] - Fo) <= TOL * abs(Fo), (N, i)
+            assert grad_err(G[i], Go, N, 1) < TOL, (N, i)
