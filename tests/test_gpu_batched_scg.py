@@ -146,6 +146,10 @@ def test_sharded_batched_scg_single_gpu_sub_batches(tmp_path):
     assert np.allclose(res["fx"], fx, rtol=1e-12) and np.array_equal(res["n_it"], opt.stats["MaxIt"])
     assert np.allclose(res["kept"][7], Xh[7], rtol=1e-12, atol=1e-14)
     assert res["sub_batch"] == 4
+    # the same sub-batches optimised concurrently (one host thread, CUDA stream and evaluator each): same results
+    res2 = ShardedBatchedSCG(B, make, opts, sub_batch=4).run(t0=0.0, keep=(0, 7), concurrent=3)
+    assert np.array_equal(res2["fx"], res["fx"]) and np.array_equal(res2["n_it"], res["n_it"])
+    assert np.array_equal(res2["kept"][7], res["kept"][7]) and res2["concurrent"] == 3
     import os
     out = ens.save(os.path.join(str(tmp_path), "ens"), N, D)
     z = load(out)

@@ -138,13 +138,16 @@ def test_small_models_at_full_size_match_oracle(oracle, model, method, N):
 
 
 @pytest.mark.parametrize("model,method,N", [("L63", "rk2", 61), ("L63", "rk4", 30), ("OU", "rk4", 75),
-                                            ("DW", "euler", 40), ("OU", "heun", 18)])
+                                            ("DW", "euler", 40), ("OU", "heun", 18), ("OU", "rk2", 75),
+                                            ("DW", "rk2", 40)])
 def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
-    """Batches above 8192 (L63) / 16384 (D = 1) problems run the staged forward sweep (small_dim.cu: blocks of time indices
-    through shared memory) and the one-thread-per-problem backward sweep; small batches run the lane-parallel
-    (L63) or time-parallel (D = 1) kernels.  A problem's result in such a batch (ragged last warp,
-    ragged last block) must agree with its result in a small batch to rounding, be bitwise independent of
-    its position inside either, and sampled rows are held to the oracle."""
+    """Large batches run other kernels than small ones.  Lorenz-63: above 8192 problems the staged forward
+    sweep (small_dim.cu: blocks of time indices through shared memory) and the one-thread-per-problem backward
+    sweep instead of the lane-parallel kernels.  D = 1: F-only evaluations above 16384 problems, and RK2 (whose
+    forward sweep is never time-parallel), take the staged forward / sequential backward sweeps; evaluations
+    with a gradient run the fused time-parallel kernel at every size.  A problem's result in such a batch
+    (ragged last warp, ragged last block) must agree with its result in a small batch to rounding, be bitwise
+    independent of its position inside either, and sampled rows are held to the oracle."""
     from vgpa_b200.engine import BatchEvaluator
     D = 3 if model == "L63" else 1
     rng = np.random.default_rng(23)
@@ -162,6 +165,8 @@ def test_large_batches_take_the_staged_forward_sweep(oracle, model, method, N):
     X = x1[None, :] + 0.05 * rng.standard_normal((B, x1.size))
     with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y, m0, s0, np.zeros(B), B=B) as ev:
         F, G = ev.eval(X)
+        F_only, _ = ev.eval(X, want_grad=False)          # D = 1: the staged forward sweep whatever the solver
+    assert np.abs(F_only - F).max() <= 1e-12 * np.abs(F).max()
     rows = np.concatenate([np.arange(0, 40), np.arange(B - 40, B)])        # first warps and the ragged last one
     with BatchEvaluator(model, method, N, 0.01, theta, sig, R, obs_t, obs_y[rows], m0[rows], s0,
                         np.zeros(rows.size), B=rows.size) as ev:

@@ -148,6 +148,11 @@ void run_chunk(vgpa_handle* h, const double* d_x, long long xs, int want_grad, d
     const Batch& b = h->batch;
     const bool small = small_model(b.model);
     h->tick(0, st, true);
+    if (small && want_grad && launch_small_fused(b, d_x, xs, d_F, d_grad, gs, p0, count, ex, st)) {
+        h->tick(0, st, false);      // the one launch is accounted to the first phase
+        h->launches += 1;
+        return;
+    }
     if (small) launch_small_fwd(b, sc, d_x, xs, p0, count, st);
     else launch_l96_fwd(b, sc, d_x, xs, p0, count, st);
     h->tick(0, st, false);
@@ -193,7 +198,13 @@ int check_status(vgpa_handle* h)
     if (!h->status_dirty) return VGPA_OK;
     h->status_dirty = false;
     std::vector<int> st(h->d.B);
-    CK(cudaMemcpy(st.data(), h->status.p, sizeof(int) * h->d.B, cudaMemcpyDeviceToHost), "cudaMemcpy(status)");
+    // Every caller has synchronised the stream that wrote the status words.  The copy runs on the handle's private
+    // NON-BLOCKING stream: a plain cudaMemcpy goes through the legacy default stream, which waits for every blocking
+    // stream of the process -- e.g. for the evaluation another host thread has in flight on another handle
+    // (ShardedBatchedSCG with concurrent sub-batches: two handles serialised each other at every status check).
+    if (h->s_aux == nullptr) CK(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking), "cudaStreamCreate");
+    CK(cudaMemcpyAsync(st.data(), h->status.p, sizeof(int) * h->d.B, cudaMemcpyDeviceToHost, h->s_aux), "cudaMemcpyAsync(status)");
+    CK(cudaStreamSynchronize(h->s_aux), "cudaStreamSynchronize(status)");
     for (int p = 0; p < h->d.B; ++p)
         if (st[p] != 0) {
             // under a compacted launch the status words are indexed by launch position

@@ -94,6 +94,10 @@ constexpr int SM_BH = 84 * 2;
 // p0: first problem of the chunk; count: problems in the chunk.
 void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,
                       int p0, int count, cudaStream_t st);
+// D = 1 batches, F and gradient wanted, nothing else kept: the whole evaluation in one launch (small_dim.cu,
+// scan1_eval_kernel).  Returns false when it does not apply; the caller then runs the four phases.
+bool launch_small_fused(const Batch& b, const double* x, long long x_stride, double* F, double* grad,
+                        long long grad_stride, int p0, int count, const Extra& ex, cudaStream_t st);
 void launch_small_energy(const Batch& b, const Scratch& s, const double* x, long long x_stride,
                          int p0, int count, const Extra& ex, cudaStream_t st);
 void launch_small_bwd(const Batch& b, const Scratch& s, const double* x, long long x_stride,

@@ -510,6 +510,25 @@ __device__ __forceinline__ void l63_energy(const double* th, const double* iS, c
     dEs[1] *= 2.0; dEs[2] *= 2.0; dEs[3] *= 2.0; dEs[5] *= 2.0; dEs[6] *= 2.0; dEs[7] *= 2.0;
 }
 
+// Esde integrand and its m, S derivatives at one time index, D = 1
+template <int MODEL>
+__device__ __forceinline__ void energy1(double th, double sg, double At, double bt, double m, double S,
+                                        double& e, double& dm, double& dS)
+{
+    if (MODEL == MODEL_DW) {  // double_well.py:214,243,248 (8*E6 in the energy, 16*Dm6 in the gradient)
+        const Moments1 g(m, S);
+        const double c = 4.0 * th + At, c2 = c * c, bb = bt;
+        e = 8.0 * (g.E6 - c * g.E4 + bb * g.E3) + (c2 * g.E2) - (2.0 * bb * c * m) + bb * bb;
+        dm = 0.5 * (16.0 * g.Dm6 - 8.0 * c * g.Dm4 + 8.0 * bb * g.Dm3 + c2 * g.Dm2 - 2.0 * bb * c) / sg;
+        dS = 0.5 * (16.0 * g.Ds6 - 8.0 * c * g.Ds4 + 8.0 * bb * g.Ds3 + c2 * 1.0) / sg;
+    } else {  // ornstein_uhlenbeck.py:205,217,221
+        const double E2 = m * m + S, d = th - At, q1 = d * d;
+        e = E2 * q1 + 2.0 * m * d * bt + bt * bt;
+        dm = (m * q1 + th * bt - At * bt) / sg;
+        dS = 0.5 * q1 / sg;
+    }
+}
+
 template <int MODEL, int D>
 __global__ void __launch_bounds__(128)
 small_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count,
@@ -534,17 +553,8 @@ small_energy_kernel(Batch b, Scratch s, const double* __restrict__ x, long long 
 #pragma unroll
     for (int i = 0; i < DD; ++i) S[i] = s.st[oM + i];
     double e, dm[D], dS[DD];
-    if (MODEL == MODEL_DW) {  // double_well.py:214,243,248 (8*E6 in the energy, 16*Dm6 in the gradient)
-        const Moments1 g(m[0], S[0]);
-        const double c = 4.0 * th[0] + At[0], c2 = c * c, bb = bt[0];
-        e = 8.0 * (g.E6 - c * g.E4 + bb * g.E3) + (c2 * g.E2) - (2.0 * bb * c * m[0]) + bb * bb;
-        dm[0] = 0.5 * (16.0 * g.Dm6 - 8.0 * c * g.Dm4 + 8.0 * bb * g.Dm3 + c2 * g.Dm2 - 2.0 * bb * c) / sg[0];
-        dS[0] = 0.5 * (16.0 * g.Ds6 - 8.0 * c * g.Ds4 + 8.0 * bb * g.Ds3 + c2 * 1.0) / sg[0];
-    } else if (MODEL == MODEL_OU) {  // ornstein_uhlenbeck.py:205,217,221
-        const double E2 = m[0] * m[0] + S[0], d = th[0] - At[0], q1 = d * d;
-        e = E2 * q1 + 2.0 * m[0] * d * bt[0] + bt[0] * bt[0];
-        dm[0] = (m[0] * q1 + th[0] * bt[0] - At[0] * bt[0]) / sg[0];
-        dS[0] = 0.5 * q1 / sg[0];
+    if constexpr (MODEL == MODEL_DW || MODEL == MODEL_OU) {
+        energy1<MODEL>(th[0], sg[0], At[0], bt[0], m[0], S[0], e, dm[0], dS[0]);
     } else {
         double iS[3] = {1.0 / sg[0], 1.0 / sg[1], 1.0 / sg[2]};
         l63_energy(th, iS, At, bt, m, S, e, dm, dS);
@@ -833,6 +843,85 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
 }
 
 // ---------------------------------------------------------------------------
+// F = E0 + Esde + Eobs : one CTA per problem, fixed-order reductions (bitwise
+// reproducible, so a sharded batch returns the same F as a single-GPU one).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh)
+{
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) sh[tid] += sh[tid + o];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// The free energy of problem p from its Esde integrand f(t) and its moments (global or shared memory); every
+// thread of the 128-thread CTA calls it, every thread gets the value.  parts: E0, Esde, Eobs (or null).
+__device__ __forceinline__ double free_energy_of(const Batch& b, int p, const double* f, const double* mt,
+                                                 const double* st, double* sh, double* parts)
+{
+    const int tid = threadIdx.x;
+    const int N = b.N, D = b.D, M = b.M, DD = D * D;
+    // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)
+    double acc = 0.0;
+    for (int i = tid; i < N - 1; i += blockDim.x) acc += b.dt_model * (f[i + 1] + f[i]) / 2.0;
+    double Esde = block_sum(acc, sh);
+    if (b.model == MODEL_DW || b.model == MODEL_OU)  // double_well.py:217, ornstein_uhlenbeck.py:208
+        Esde = 0.5 * Esde / b.sigma[p * b.sigma_stride];
+    // observation energy
+    const double* oy = b.obs_y + p * b.obs_y_stride;
+    const double* R = b.R + p * b.R_stride;
+    double Eobs;
+    const double LOG2PI = 1.8378770664093453;
+    if (D == 1) {  // gaussian_like.py:69-96
+        acc = 0.0;
+        for (int n = tid; n < M; n += blockDim.x) {
+            const long long t = b.obs_t[n];
+            const double y = oy[n], E2 = mt[t] * mt[t] + st[t];
+            acc += (y * y) - 2.0 * y * mt[t] + E2;
+        }
+        const double sm = block_sum(acc, sh);
+        Eobs = 0.5 * sm / R[0] + 0.5 * M * (LOG2PI + log(R[0]));
+    } else {  // gaussian_like.py:98-153; S diagonal indexed by the observation ORDINAL n
+        acc = 0.0;
+        for (int q = tid; q < M * D; q += blockDim.x) {
+            const int n = q / D, i = q % D;
+            const long long t = b.obs_t[n];
+            const double z = (oy[(long long)n * D + i] - mt[t * D + i]) / sqrt(R[i]);
+            acc += z * z + (1.0 / R[i]) * st[(long long)n * DD + (long long)i * D + i];
+        }
+        const double sm = block_sum(acc, sh);
+        double ld = 0.0;
+        for (int i = 0; i < D; ++i) ld += log(sqrt(R[i]));
+        Eobs = 0.5 * (sm + M * (D * LOG2PI + 2.0 * ld));
+    }
+    const double E0 = b.E0[p * b.E0_stride];
+    if (parts != nullptr && tid == 0) {
+        parts[0] = E0;
+        parts[1] = Esde;
+        parts[2] = Eobs;
+    }
+    return E0 + Esde + Eobs;
+}
+
+__global__ void __launch_bounds__(128)
+finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, Extra ex)
+{
+    __shared__ double sh[128];
+    const int lp = blockIdx.x, p = problem_at(b, p0 + lp);
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    const int N = b.N, D = b.D;
+    const double Fp = free_energy_of(b, p, s.esde_t + (long long)lp * N, s.mt + (long long)lp * N * D,
+                                     s.st + (long long)lp * N * D * D, sh, lp == 0 ? ex.parts : nullptr);
+    if (threadIdx.x == 0) F[p] = Fp;
+}
+
+// ---------------------------------------------------------------------------
 // D = 1 (DW, OU), small batches: time-parallel sweeps, one 128-thread CTA per problem.
 //
 // With one thread per problem the sweeps above are a chain of N-1 dependent solver steps (~450 cycles
@@ -852,8 +941,10 @@ small_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count, Extra ex
 // states differ from the sequential kernels (rounding of the composed maps, ~1e-16 relative per step);
 // inside a run the arithmetic is the sequential one.
 // ---------------------------------------------------------------------------
-constexpr int SCAN_MAX_BATCH = 16384;     // above: one thread per problem fills the FP64 pipe better (measured, OU rk4:
-                                          // 12.4 M evaluations/s time-parallel at 8192 problems, 14.5 M/s sequential at 65536)
+constexpr int SCAN_MAX_BATCH = 16384;     // the separate sweeps (F only; RK2's backward sweep): above, one thread per problem
+                                          // fills the FP64 pipe better.  The fused evaluation (scan1_eval_kernel) has no such
+                                          // limit: measured faster than the sequential kernels at every batch size
+                                          // (OU rk4 x 65536: 4.21 against 4.51 ms)
 constexpr int SCAN_THREADS = 128;
 constexpr size_t SCAN_MAX_SMEM = 200 * 1024;
 
@@ -886,27 +977,16 @@ __device__ __forceinline__ void stage_array(double* __restrict__ dst, const doub
     for (int i = threadIdx.x; i < n; i += SCAN_THREADS) dst[i] = __ldg(src + i);
 }
 
+// forward sweep of one problem: A, bo in shared memory; mt, st (N each) in shared or global memory
 template <int METHOD>
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan1_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count)
+__device__ __forceinline__ void scan1_fwd_body(const double* A, const double* bo, int N, double sig, double dt,
+                                               double m0, double S0, double* mt, double* st, Affine (*sh)[SCAN_THREADS / 32])
 {
     static_assert(METHOD != ODE_RK2, "RK2's forward variance stage is quadratic in S");
-    extern __shared__ double scan_sm[];
-    __shared__ Affine sh[2][SCAN_THREADS / 32];
-    const int lp = blockIdx.x, tid = threadIdx.x;
-    const int p = p0 + lp, N = b.N;
-    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
-    double* A = scan_sm;
-    double* bo = A + N;
-    stage_array(A, x + (long long)p * xs, 2 * N);          // A then b, contiguous in x
-    const double sig = b.sigma[p * b.sigma_stride], dt = b.dt;
-    const double m0 = b.m0[p * b.m0_stride], S0 = b.s0[p * b.s0_stride];
-    double* mt = s.mt + (long long)lp * N;
-    double* st = s.st + (long long)lp * N;
+    const int tid = threadIdx.x;
     const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
     const int k0 = min(tid * L, steps), k1 = min(k0 + L, steps);
     const double zero = 0.0, one = 1.0;
-    __syncthreads();
     Affine fm{1.0, 0.0}, fS{1.0, 0.0};
     for (int k = k0; k < k1; ++k) {
         double qm, qS, rm, rS;
@@ -932,28 +1012,14 @@ scan1_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
     }
 }
 
+// backward sweep and gradient of one problem: A, bo, mt, st, dEm, dEs in shared memory; gA, gb in global memory
 template <int MODEL, int METHOD>
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan1_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count)
+__device__ __forceinline__ void scan1_bwd_body(const Batch& b, int p, const double* A, const double* bo,
+                                               const double* mt, const double* st, const double* dEm,
+                                               const double* dEs, double* gA, double* gb,
+                                               Affine (*sh)[SCAN_THREADS / 32])
 {
-    extern __shared__ double scan_sm[];
-    __shared__ Affine sh[2][SCAN_THREADS / 32];
-    const int lp = blockIdx.x, tid = threadIdx.x;
-    const int p = p0 + lp, N = b.N;
-    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
-    double* A = scan_sm;
-    double* bo = A + N;
-    double* mt = bo + N;
-    double* st = mt + N;
-    double* dEm = st + N;
-    double* dEs = dEm + N;
-    stage_array(A, a.x + (long long)p * a.xs, 2 * N);
-    stage_array(mt, s.mt + (long long)lp * N, N);
-    stage_array(st, s.st + (long long)lp * N, N);
-    stage_array(dEm, s.dEm + (long long)lp * N, N);
-    stage_array(dEs, s.dEs + (long long)lp * N, N);
-    double* gA = a.grad + (long long)p * a.gs;
-    double* gb = gA + N;
+    const int tid = threadIdx.x, N = b.N;
     const double* th = b.theta + p * b.theta_stride;
     const double* oy = b.obs_y + p * b.obs_y_stride;
     const double isg = 1.0 / b.sigma[p * b.sigma_stride], Rv = b.R[p * b.R_stride];
@@ -962,7 +1028,6 @@ scan1_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count)
     const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
     const int q0 = min(tid * L, steps), q1 = min(q0 + L, steps);
     const double zero = 0.0, one = 1.0;
-    __syncthreads();
 
     // jump of lambda and Psi at index t (gaussian_like.py:188,191), as in small_bwd_kernel
     auto jump = [&](int t, double& jm, double& js) {
@@ -1007,82 +1072,84 @@ scan1_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count)
     // index 0: the thread that took the last step (thread 0 when the grid has a single point)
     if ((steps == 0) ? (tid == 0) : (q0 < q1 && q1 == steps)) grad(0);
 }
+
+template <int METHOD>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs, int p0, int count)
+{
+    extern __shared__ double scan_sm[];
+    __shared__ Affine sh[2][SCAN_THREADS / 32];
+    const int lp = blockIdx.x;
+    const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    double* A = scan_sm;
+    stage_array(A, x + (long long)p * xs, 2 * N);          // A then b, contiguous in x
+    __syncthreads();
+    scan1_fwd_body<METHOD>(A, A + N, N, b.sigma[p * b.sigma_stride], b.dt, b.m0[p * b.m0_stride], b.s0[p * b.s0_stride],
+                           s.mt + (long long)lp * N, s.st + (long long)lp * N, sh);
+}
+
+template <int MODEL, int METHOD>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_bwd_kernel(Batch b, Scratch s, SmallBwdArgs a, int p0, int count)
+{
+    extern __shared__ double scan_sm[];
+    __shared__ Affine sh[2][SCAN_THREADS / 32];
+    const int lp = blockIdx.x;
+    const int p = p0 + lp, N = b.N;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    double* A = scan_sm;
+    double* mt = A + 2 * N;
+    double* st = mt + N;
+    double* dEm = st + N;
+    double* dEs = dEm + N;
+    stage_array(A, a.x + (long long)p * a.xs, 2 * N);
+    stage_array(mt, s.mt + (long long)lp * N, N);
+    stage_array(st, s.st + (long long)lp * N, N);
+    stage_array(dEm, s.dEm + (long long)lp * N, N);
+    stage_array(dEs, s.dEs + (long long)lp * N, N);
+    __syncthreads();
+    double* gA = a.grad + (long long)p * a.gs;
+    scan1_bwd_body<MODEL, METHOD>(b, p, A, A + N, mt, st, dEm, dEs, gA, gA + N, sh);
+}
+
+// The whole evaluation of one problem in ONE launch (F and the gradient wanted, no trajectories kept): forward
+// sweep, Esde integrand and its derivatives, F, backward sweep and gradient, with m, S, dE/dm, dE/dS and the
+// integrand living in shared memory only -- HBM sees x once (16 N bytes) and the gradient once.
+template <int MODEL, int METHOD>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_eval_kernel(Batch b, const double* __restrict__ x, long long xs, double* __restrict__ F,
+                  double* __restrict__ grad, long long gs, int p0, int count)
+{
+    extern __shared__ double scan_sm[];
+    __shared__ Affine sh[2][SCAN_THREADS / 32];
+    __shared__ double red[SCAN_THREADS];
+    const int p = p0 + blockIdx.x, N = b.N, tid = threadIdx.x;
+    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
+    double* A = scan_sm;
+    double* bo = A + N;
+    double* mt = bo + N;
+    double* st = mt + N;
+    double* dEm = st + N;
+    double* dEs = dEm + N;
+    double* ft = dEs + N;
+    stage_array(A, x + (long long)p * xs, 2 * N);
+    const double sig = b.sigma[p * b.sigma_stride], th0 = b.theta[p * b.theta_stride];
+    __syncthreads();
+    scan1_fwd_body<METHOD>(A, bo, N, sig, b.dt, b.m0[p * b.m0_stride], b.s0[p * b.s0_stride], mt, st, sh);
+    __syncthreads();
+    for (int t = tid; t < N; t += SCAN_THREADS) energy1<MODEL>(th0, sig, A[t], bo[t], mt[t], st[t], ft[t], dEm[t], dEs[t]);
+    __syncthreads();
+    const double Fp = free_energy_of(b, p, ft, mt, st, red, nullptr);
+    if (tid == 0) F[p] = Fp;
+    double* gA = grad + (long long)p * gs;
+    scan1_bwd_body<MODEL, METHOD>(b, p, A, bo, mt, st, dEm, dEs, gA, gA + N, sh);
+}
 // shared memory of the two kernels for a grid of N points; the launchers fall back to the sequential
 // kernels when it does not fit
 static inline size_t scan_fwd_bytes(int N) { return sizeof(double) * 2 * (size_t)N; }
 static inline size_t scan_bwd_bytes(int N) { return sizeof(double) * 6 * (size_t)N; }
-
-// ---------------------------------------------------------------------------
-// F = E0 + Esde + Eobs : one CTA per problem, fixed-order reductions (bitwise
-// reproducible, so a sharded batch returns the same F as a single-GPU one).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* sh)
-{
-    const int tid = threadIdx.x;
-    sh[tid] = v;
-    __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (tid < o) sh[tid] += sh[tid + o];
-        __syncthreads();
-    }
-    const double r = sh[0];
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(128)
-finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, Extra ex)
-{
-    __shared__ double sh[128];
-    const int lp = blockIdx.x, p = problem_at(b, p0 + lp), tid = threadIdx.x;
-    if (b.active != nullptr && b.active[p] == 0) return;   // the whole CTA: before any barrier
-    const int N = b.N, D = b.D, M = b.M, DD = D * D;
-    // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)
-    const double* f = s.esde_t + (long long)lp * N;
-    double acc = 0.0;
-    for (int i = tid; i < N - 1; i += blockDim.x) acc += b.dt_model * (f[i + 1] + f[i]) / 2.0;
-    double Esde = block_sum(acc, sh);
-    if (b.model == MODEL_DW || b.model == MODEL_OU)  // double_well.py:217, ornstein_uhlenbeck.py:208
-        Esde = 0.5 * Esde / b.sigma[p * b.sigma_stride];
-    // observation energy
-    const double* mt = s.mt + (long long)lp * N * D;
-    const double* st = s.st + (long long)lp * N * DD;
-    const double* oy = b.obs_y + p * b.obs_y_stride;
-    const double* R = b.R + p * b.R_stride;
-    double Eobs;
-    const double LOG2PI = 1.8378770664093453;
-    if (D == 1) {  // gaussian_like.py:69-96
-        acc = 0.0;
-        for (int n = tid; n < M; n += blockDim.x) {
-            const long long t = b.obs_t[n];
-            const double y = oy[n], E2 = mt[t] * mt[t] + st[t];
-            acc += (y * y) - 2.0 * y * mt[t] + E2;
-        }
-        const double sm = block_sum(acc, sh);
-        Eobs = 0.5 * sm / R[0] + 0.5 * M * (LOG2PI + log(R[0]));
-    } else {  // gaussian_like.py:98-153; S diagonal indexed by the observation ORDINAL n
-        acc = 0.0;
-        for (int q = tid; q < M * D; q += blockDim.x) {
-            const int n = q / D, i = q % D;
-            const long long t = b.obs_t[n];
-            const double z = (oy[(long long)n * D + i] - mt[t * D + i]) / sqrt(R[i]);
-            acc += z * z + (1.0 / R[i]) * st[(long long)n * DD + (long long)i * D + i];
-        }
-        const double sm = block_sum(acc, sh);
-        double ld = 0.0;
-        for (int i = 0; i < D; ++i) ld += log(sqrt(R[i]));
-        Eobs = 0.5 * (sm + M * (D * LOG2PI + 2.0 * ld));
-    }
-    if (tid == 0) {
-        const double E0 = b.E0[p * b.E0_stride];
-        F[p] = E0 + Esde + Eobs;
-        if (ex.parts != nullptr && lp == 0) {
-            ex.parts[0] = E0;
-            ex.parts[1] = Esde;
-            ex.parts[2] = Eobs;
-        }
-    }
-}
+static inline size_t scan_eval_bytes(int N) { return sizeof(double) * 7 * (size_t)N; }
 
 // ---------------------------------------------------------------------------
 // launchers
@@ -1141,6 +1208,36 @@ void launch_small_fwd(const Batch& b, const Scratch& s, const double* x, long lo
     if (b.D == 1) fwd_dispatch<1>(b, s, x, xs, p0, count, st);
     else if (l63_lanes_applies(b, count)) launch_l63_fwd_lanes(b, s, x, xs, p0, count, st);
     else          fwd_dispatch<3>(b, s, x, xs, p0, count, st);
+}
+
+// D = 1, F and gradient, nothing kept: one launch per pass.  False: not applicable (the caller runs the phases).
+bool launch_small_fused(const Batch& b, const double* x, long long xs, double* F, double* g, long long gs,
+                        int p0, int count, const Extra& ex, cudaStream_t st)
+{
+    const size_t sh = scan_eval_bytes(b.N);
+    if (b.D != 1 || g == nullptr || b.method == ODE_RK2 || sh > SCAN_MAX_SMEM ||
+        ex.lamt != nullptr || ex.Efx != nullptr || ex.parts != nullptr)
+        return false;
+#define VGPA_SCAN_EVAL(MODEL, M)                                                                                  \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(scan1_eval_kernel<MODEL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);  \
+        scan1_eval_kernel<MODEL, M><<<count, SCAN_THREADS, sh, st>>>(b, x, xs, F, g, gs, p0, count);              \
+    } while (0)
+    if (b.model == MODEL_DW) {
+        switch (b.method) {
+        case ODE_EULER: VGPA_SCAN_EVAL(MODEL_DW, ODE_EULER); break;
+        case ODE_HEUN:  VGPA_SCAN_EVAL(MODEL_DW, ODE_HEUN); break;
+        default:        VGPA_SCAN_EVAL(MODEL_DW, ODE_RK4); break;
+        }
+    } else {
+        switch (b.method) {
+        case ODE_EULER: VGPA_SCAN_EVAL(MODEL_OU, ODE_EULER); break;
+        case ODE_HEUN:  VGPA_SCAN_EVAL(MODEL_OU, ODE_HEUN); break;
+        default:        VGPA_SCAN_EVAL(MODEL_OU, ODE_RK4); break;
+        }
+    }
+#undef VGPA_SCAN_EVAL
+    return true;
 }
 
 void launch_small_energy(const Batch& b, const Scratch& s, const double* x, long long xs, int p0,
