@@ -110,3 +110,52 @@ def test_time_parallel_sweeps_at_run_boundaries(oracle, model, method):
             Fo, Go = oracle.eval(prob, X[i])
             assert abs(F[i] - Fo) <= TOL * abs(Fo), (N, i)
             assert grad_err(G[i], Go, N, 1) < TOL, (N, i)
+
+
+_FAMILY_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from vgpa_b200.engine import BatchEvaluator
+z = np.load(sys.argv[2])
+out = {}
+for model in ("DW", "OU"):
+    for method in ("euler", "heun", "rk2", "rk4"):
+        with BatchEvaluator(model, method, int(z["N"]), 0.01, z["theta_" + model], z["sigma"], z["R"], z["obs_t"], z["obs_y"],
+                            z["m0"], z["s0"], z["E0"], B=int(z["B"])) as ev:
+            F, G = ev.eval(z["X"])
+            F1, _ = ev.eval(z["X"], want_grad=False)
+        out[f"F_{model}_{method}"], out[f"G_{model}_{method}"], out[f"F1_{model}_{method}"] = F, G, F1
+np.savez(sys.argv[3], **out)
+"""
+
+
+def test_time_parallel_and_sequential_kernel_families_agree(tmp_path):
+    """The same D = 1 problems (N = 1001, every model and solver) through the time-parallel kernels and, in a second
+    process with VGPA_SEQUENTIAL_D1=1, through the one-thread-per-problem kernels: F and the gradient agree to
+    rounding (the run-start states of the time-parallel sweeps come out of a scan), far inside the 1e-9 bar that
+    both hold against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(31)
+    N, B, M = 1001, 5, 20
+    obs_t = np.linspace(0, N, M + 2, dtype=int)[1:-1].astype(np.int64)
+    inp = dict(N=N, B=B, theta_DW=np.array([1.0]), theta_OU=np.array([2.0]), sigma=rng.uniform(0.5, 1.2, (B, 1)),
+               R=rng.uniform(0.03, 0.08, (B, 1)), obs_t=obs_t, obs_y=0.7 * rng.standard_normal((B, M, 1)),
+               m0=rng.standard_normal((B, 1)), s0=rng.uniform(0.2, 0.4, (B, 1, 1)), E0=rng.standard_normal(B),
+               X=np.concatenate([1.6 + 0.2 * rng.standard_normal((B, N)), 0.3 * rng.standard_normal((B, N))], axis=1))
+    fin = os.path.join(str(tmp_path), "in.npz")
+    np.savez(fin, **inp)
+    res = {}
+    for tag, flag in (("scan", "0"), ("seq", "1")):
+        fout = os.path.join(str(tmp_path), tag + ".npz")
+        env = dict(os.environ, VGPA_SEQUENTIAL_D1=flag)
+        subprocess.run([sys.executable, "-c", _FAMILY_SCRIPT, root, fin, fout], check=True, env=env, timeout=600)
+        res[tag] = np.load(fout)
+    differ = 0
+    for key in res["scan"].files:
+        a, b = res["scan"][key], res["seq"][key]
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), key
+        differ += int(not np.array_equal(a, b))
+    assert differ > 0          # the switch did select another kernel family

@@ -12,6 +12,8 @@
 //   jumps           src/var_bayes/gaussian_like.py:155-243
 //   gradient        src/var_bayes/variational.py:202-334
 //   F               variational.py:199, utilities.py:144-201, gaussian_like.py:69-153
+#include <cstdlib>
+
 #include "common.cuh"
 #include "l63_grad.cuh"
 
@@ -945,7 +947,17 @@ constexpr int SCAN_MAX_BATCH = 16384;     // the separate sweeps (F only; RK2's 
                                           // fills the FP64 pipe better.  The fused evaluation (scan1_eval_kernel) has no such
                                           // limit: measured faster than the sequential kernels at every batch size
                                           // (OU rk4 x 65536: 4.21 against 4.51 ms)
+constexpr int SCAN_RK2_MAX_BATCH = 8192;  // RK2's forward sweep keeps one serial recurrence per problem (scan1_fwd_body): measured
+                                          // against one thread per problem, OU rk2: 1024 problems 0.158 / 0.79 ms, 8192 1.00 / 1.11,
+                                          // 16384 1.95 / 1.37, 65536 7.7 / 4.1
 constexpr int SCAN_THREADS = 128;
+// VGPA_SEQUENTIAL_D1=1 in the environment: D = 1 batches take the one-thread-per-problem kernels whatever their size
+// (a diagnostic switch: A/B timings, and tests that compare the two kernel families on the same problems)
+static bool scan_disabled()
+{
+    static const bool off = [] { const char* e = getenv("VGPA_SEQUENTIAL_D1"); return e != nullptr && e[0] == '1'; }();
+    return off;
+}
 constexpr size_t SCAN_MAX_SMEM = 200 * 1024;
 
 struct Affine { double P, Q; };           // y -> P y + Q
@@ -977,27 +989,59 @@ __device__ __forceinline__ void stage_array(double* __restrict__ dst, const doub
     for (int i = threadIdx.x; i < n; i += SCAN_THREADS) dst[i] = __ldg(src + i);
 }
 
-// forward sweep of one problem: A, bo in shared memory; mt, st (N each) in shared or global memory
+// forward sweep of one problem: A, bo in shared memory; mt, st (N each) in shared or global memory.
+// coef: 3 N doubles of shared memory, used by RK2 only.  RK2's variance stage passes S in place of A
+// (runge_kutta2.py:92), which makes its step a QUADRATIC map S -> a S^2 + b S + c: no scan composes those.  Its
+// coefficients still depend on A(t) only, so every thread finds them for its run (the solver step applied to
+// S = 0, 1, -1), ONE thread then runs the 2-FMA recurrence over the whole grid (~25 cycles per step instead of the
+// solver step's ~300) noting S at the start of every run, and the runs are walked from there as for the other
+// solvers.  The mean is affine for every solver.
 template <int METHOD>
 __device__ __forceinline__ void scan1_fwd_body(const double* A, const double* bo, int N, double sig, double dt,
-                                               double m0, double S0, double* mt, double* st, Affine (*sh)[SCAN_THREADS / 32])
+                                               double m0, double S0, double* mt, double* st, double* coef,
+                                               Affine (*sh)[SCAN_THREADS / 32])
 {
-    static_assert(METHOD != ODE_RK2, "RK2's forward variance stage is quadratic in S");
+    __shared__ double run_start[SCAN_THREADS];
     const int tid = threadIdx.x;
     const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
     const int k0 = min(tid * L, steps), k1 = min(k0 + L, steps);
-    const double zero = 0.0, one = 1.0;
+    const double zero = 0.0, one = 1.0, minus = -1.0;
     Affine fm{1.0, 0.0}, fS{1.0, 0.0};
     for (int k = k0; k < k1; ++k) {
         double qm, qS, rm, rS;
         fwd_step<1, METHOD>(&zero, &zero, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &qm, &qS);
         fwd_step<1, METHOD>(&one, &one, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &rm, &rS);
         fm = after(Affine{rm - qm, qm}, fm);
-        fS = after(Affine{rS - qS, qS}, fS);
+        if constexpr (METHOD == ODE_RK2) {
+            double um, uS;
+            fwd_step<1, METHOD>(&zero, &minus, A + k, bo + k, A + k + 1, bo + k + 1, &sig, dt, &um, &uS);
+            coef[3 * k + 0] = 0.5 * (rS + uS) - qS;      // a
+            coef[3 * k + 1] = 0.5 * (rS - uS);           // b
+            coef[3 * k + 2] = qS;                        // c
+        } else {
+            fS = after(Affine{rS - qS, qS}, fS);
+        }
     }
-    const Affine em = scan_exclusive(fm, sh[0]), eS = scan_exclusive(fS, sh[1]);
+    const Affine em = scan_exclusive(fm, sh[0]);         // (contains block barriers: coef is visible after it)
     double m = (tid == 0) ? m0 : fma(em.P, m0, em.Q);
-    double S = (tid == 0) ? S0 : fma(eS.P, S0, eS.Q);
+    double S;
+    if constexpr (METHOD == ODE_RK2) {
+        if (tid == 0) {
+            double Sq = S0;
+            const double* c = coef;
+            for (int r = 0, k = 0; k < steps; ++r) {
+                run_start[r] = Sq;
+                const int ke = min(k + L, steps);
+#pragma unroll 4
+                for (; k < ke; ++k, c += 3) Sq = fma(fma(c[0], Sq, c[1]), Sq, c[2]);
+            }
+        }
+        __syncthreads();
+        S = (k0 < k1) ? run_start[tid] : 0.0;
+    } else {
+        const Affine eS = scan_exclusive(fS, sh[1]);
+        S = (tid == 0) ? S0 : fma(eS.P, S0, eS.Q);
+    }
     if (tid == 0) {
         mt[0] = m0;
         st[0] = S0;
@@ -1086,7 +1130,7 @@ scan1_fwd_kernel(Batch b, Scratch s, const double* __restrict__ x, long long xs,
     stage_array(A, x + (long long)p * xs, 2 * N);          // A then b, contiguous in x
     __syncthreads();
     scan1_fwd_body<METHOD>(A, A + N, N, b.sigma[p * b.sigma_stride], b.dt, b.m0[p * b.m0_stride], b.s0[p * b.s0_stride],
-                           s.mt + (long long)lp * N, s.st + (long long)lp * N, sh);
+                           s.mt + (long long)lp * N, s.st + (long long)lp * N, A + 2 * N, sh);
 }
 
 template <int MODEL, int METHOD>
@@ -1136,7 +1180,7 @@ scan1_eval_kernel(Batch b, const double* __restrict__ x, long long xs, double* _
     stage_array(A, x + (long long)p * xs, 2 * N);
     const double sig = b.sigma[p * b.sigma_stride], th0 = b.theta[p * b.theta_stride];
     __syncthreads();
-    scan1_fwd_body<METHOD>(A, bo, N, sig, b.dt, b.m0[p * b.m0_stride], b.s0[p * b.s0_stride], mt, st, sh);
+    scan1_fwd_body<METHOD>(A, bo, N, sig, b.dt, b.m0[p * b.m0_stride], b.s0[p * b.s0_stride], mt, st, dEm, sh);   // dEm, dEs, ft: free until the energy phase
     __syncthreads();
     for (int t = tid; t < N; t += SCAN_THREADS) energy1<MODEL>(th0, sig, A[t], bo[t], mt[t], st[t], ft[t], dEm[t], dEs[t]);
     __syncthreads();
@@ -1147,7 +1191,7 @@ scan1_eval_kernel(Batch b, const double* __restrict__ x, long long xs, double* _
 }
 // shared memory of the two kernels for a grid of N points; the launchers fall back to the sequential
 // kernels when it does not fit
-static inline size_t scan_fwd_bytes(int N) { return sizeof(double) * 2 * (size_t)N; }
+static inline size_t scan_fwd_bytes(int N, int method) { return sizeof(double) * (method == ODE_RK2 ? 5 : 2) * (size_t)N; }
 static inline size_t scan_bwd_bytes(int N) { return sizeof(double) * 6 * (size_t)N; }
 static inline size_t scan_eval_bytes(int N) { return sizeof(double) * 7 * (size_t)N; }
 
@@ -1159,8 +1203,8 @@ static void fwd_dispatch(const Batch& b, const Scratch& s, const double* x, long
                          int count, cudaStream_t st)
 {
     if constexpr (D == 1) {
-        const size_t sh = scan_fwd_bytes(b.N);
-        if (count <= SCAN_MAX_BATCH && b.method != ODE_RK2 && sh <= SCAN_MAX_SMEM) {   // time-parallel
+        const size_t sh = scan_fwd_bytes(b.N, b.method);
+        if (count <= (b.method == ODE_RK2 ? SCAN_RK2_MAX_BATCH : SCAN_MAX_BATCH) && sh <= SCAN_MAX_SMEM && !scan_disabled()) {
 #define VGPA_SCAN_FWD(M)                                                                                  \
     do {                                                                                                  \
         cudaFuncSetAttribute(scan1_fwd_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);  \
@@ -1169,6 +1213,7 @@ static void fwd_dispatch(const Batch& b, const Scratch& s, const double* x, long
             switch (b.method) {
             case ODE_EULER: VGPA_SCAN_FWD(ODE_EULER); break;
             case ODE_HEUN:  VGPA_SCAN_FWD(ODE_HEUN); break;
+            case ODE_RK2:   VGPA_SCAN_FWD(ODE_RK2); break;
             default:        VGPA_SCAN_FWD(ODE_RK4); break;
             }
 #undef VGPA_SCAN_FWD
@@ -1215,7 +1260,8 @@ bool launch_small_fused(const Batch& b, const double* x, long long xs, double* F
                         int p0, int count, const Extra& ex, cudaStream_t st)
 {
     const size_t sh = scan_eval_bytes(b.N);
-    if (b.D != 1 || g == nullptr || b.method == ODE_RK2 || sh > SCAN_MAX_SMEM ||
+    if (b.D != 1 || g == nullptr || sh > SCAN_MAX_SMEM || scan_disabled() ||
+        (b.method == ODE_RK2 && count > SCAN_RK2_MAX_BATCH) ||
         ex.lamt != nullptr || ex.Efx != nullptr || ex.parts != nullptr)
         return false;
 #define VGPA_SCAN_EVAL(MODEL, M)                                                                                  \
@@ -1227,12 +1273,14 @@ bool launch_small_fused(const Batch& b, const double* x, long long xs, double* F
         switch (b.method) {
         case ODE_EULER: VGPA_SCAN_EVAL(MODEL_DW, ODE_EULER); break;
         case ODE_HEUN:  VGPA_SCAN_EVAL(MODEL_DW, ODE_HEUN); break;
+        case ODE_RK2:   VGPA_SCAN_EVAL(MODEL_DW, ODE_RK2); break;
         default:        VGPA_SCAN_EVAL(MODEL_DW, ODE_RK4); break;
         }
     } else {
         switch (b.method) {
         case ODE_EULER: VGPA_SCAN_EVAL(MODEL_OU, ODE_EULER); break;
         case ODE_HEUN:  VGPA_SCAN_EVAL(MODEL_OU, ODE_HEUN); break;
+        case ODE_RK2:   VGPA_SCAN_EVAL(MODEL_OU, ODE_RK2); break;
         default:        VGPA_SCAN_EVAL(MODEL_OU, ODE_RK4); break;
         }
     }
@@ -1258,7 +1306,7 @@ static void bwd_dispatch(const Batch& b, const Scratch& s, const SmallBwdArgs& a
     if constexpr (D == 1) {
         const size_t sh = scan_bwd_bytes(b.N);
         if (a.grad != nullptr && a.jm_dense == nullptr && ex.lamt == nullptr && count <= SCAN_MAX_BATCH &&
-            sh <= SCAN_MAX_SMEM) {   // time-parallel
+            sh <= SCAN_MAX_SMEM && !scan_disabled()) {   // time-parallel
 #define VGPA_SCAN_BWD(M)                                                                                        \
     do {                                                                                                        \
         cudaFuncSetAttribute(scan1_bwd_kernel<MODEL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
