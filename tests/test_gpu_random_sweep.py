@@ -83,14 +83,15 @@ def test_random_configurations_match_oracle(oracle, model, method):
 def test_time_parallel_sweeps_at_run_boundaries(oracle, model, method):
     """The D = 1 time-parallel sweeps (small_dim.cu, scan1_*) cut the N-1 steps into 128 runs: grid lengths
     with fewer steps than threads (2, 3, 100), exactly one step per thread and one more (129, 130), ragged
-    last runs (300, 1538), and a grid too long for shared memory (4300: the sequential kernels), each with
+    last runs (300, 1538), a grid too long for the fused kernel's shared memory but not for the separate
+    time-parallel sweeps (3800) and one too long for those as well (4300: the sequential kernels), each with
     observations on both ends of the grid and on neighbouring indices, against the oracle."""
     from oracle import Problem
     from vgpa_b200.engine import BatchEvaluator
     rng = np.random.default_rng([23, {"euler": 0, "heun": 1, "rk2": 2, "rk4": 3}[method], model == "OU"])
     theta = np.array([2.0] if model == "OU" else [1.0])
     B = 3
-    for N in (2, 3, 100, 129, 130, 300, 1538, 4300):
+    for N in (2, 3, 100, 129, 130, 300, 1538, 3800, 4300):
         M = min(N, 12)
         obs_t = np.unique(np.concatenate([[0, N - 1], [N // 2, min(N // 2 + 1, N - 1)],
                                           rng.choice(N, size=M, replace=False)])).astype(np.int64)
