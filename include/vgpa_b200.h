@@ -265,7 +265,8 @@ int vgpa_bstats(int B, int64_t n, const double *x, int64_t stride, double *out2B
  * launch of vgpa_eval / vgpa_eval_device is bracketed by CUDA events on the
  * launching stream.  vgpa_get_timing synchronises, then returns the accumulated
  * milliseconds and launch counts per kernel kind and clears the accumulators:
- *   kind 0 forward sweep, 1 time-parallel energy, 2 finalize (F), 3 backward+gradient. */
+ *   kind 0 forward sweep, 1 time-parallel energy, 2 finalize (F), 3 backward+gradient.
+ * (D = 1 evaluations with a gradient are ONE launch doing all four: accounted to kind 0.) */
 int vgpa_set_timing(vgpa_handle *h, int enable);
 int vgpa_get_timing(vgpa_handle *h, double ms[4], int64_t launches[4]);
 const char *vgpa_version(void);
