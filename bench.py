@@ -466,6 +466,10 @@ def secondary_configs(torch, local, hbm_peak, with_reference=True):
                                   "frac": round(gbs / hbm_peak, 4)},
                      "l2": ("working set (x + grad) %.0f MB: %s" % (Bn * 2 * 8.0 * nx / 1e6, "larger than the 126 MB L2"
                             if Bn * 2 * 8.0 * nx > 126e6 else "fits the 126 MB L2 (not flushed between iterations: stated)"))}
+        if Dm == 1:
+            out[name]["note"] = ("one fused time-parallel launch per evaluation (small_dim.cu scan1_eval_kernel): HBM sees x and "
+                                 "the gradient only, 2/9 of the three-phase byte count the roofline entry is computed from; "
+                                 "the kernel is bound by the FP64 pipe and its barriers, not by HBM")
         del X, G, F
 
     batch("OU_x1024_rk4_N1001", base("OU", "RK4", 10.0, 0.8, 0.04, 2, 2.0), 1024)
