@@ -390,9 +390,11 @@ class ShardedBatchedSCG:
                     else:
                         x0_fn(lo_, hi_, X)
                     opt = BatchedSCG(ev, self.options)
+                    t_opt = time.perf_counter()
                     Xf, fxb = opt(X, adopt=True)
                     stream.synchronize()
-                    res = {"range": rng_, "fx": fxb, "n_it": opt.stats["MaxIt"], "f_eval": opt.stats["f_eval"],
+                    t_opt = time.perf_counter() - t_opt
+                    res = {"range": rng_, "optimise_seconds": t_opt, "fx": fxb, "n_it": opt.stats["MaxIt"], "f_eval": opt.stats["f_eval"],
                            "evaluations": opt.stats["evaluations"] * b, "syncs": opt.host_syncs,
                            "kept": {k: Xf[k - lo_].cpu().numpy() for k in keep if lo_ <= k < hi_}}
                     del opt, Xf, X
@@ -414,12 +416,13 @@ class ShardedBatchedSCG:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         seconds = time.perf_counter() - t_
-        evaluations, syncs = 0, 0
+        evaluations, syncs, optimise_seconds = 0, 0, 0.0
         for r in results:
             sl = slice(r["range"][0] - self.lo, r["range"][1] - self.lo)
             fx[sl], n_it[sl], f_eval[sl] = r["fx"], r["n_it"], r["f_eval"]
             evaluations += r["evaluations"]
             syncs += r["syncs"]
+            optimise_seconds += r["optimise_seconds"]
             kept.update(r["kept"])
         # gather of the per-problem results (the only collective)
         def gather(v):
@@ -428,7 +431,7 @@ class ShardedBatchedSCG:
             from .ensemble import gather_free_energies
             return gather_free_energies(np.asarray(v, dtype=np.float64), self.total, self.group)
         out = {"fx": gather(fx), "n_it": gather(n_it.astype(np.float64)).astype(np.int64), "f_eval": gather(f_eval),
-               "rank_seconds": seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
+               "rank_seconds": seconds, "rank_optimise_seconds": optimise_seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
                "sub_batch": sub, "concurrent": concurrent, "kept": kept}
         self.result = out
         return out
