@@ -19,6 +19,7 @@ def _load(name):
 @pytest.mark.parametrize("name,max_it", [("eval_OU_rk4", 60), ("eval_DW_euler", 60), ("eval_L63_heun", 40),
                                           ("eval_L96_rk2", 12)])
 def test_batched_scg_follows_single_problem_scg(name, max_it):
+    from conftest import stop_tolerance
     from oracle import prior_kl0
     from vgpa_b200.batched_scg import BatchedSCG
     from vgpa_b200.engine import BatchEvaluator
@@ -49,7 +50,9 @@ def test_batched_scg_follows_single_problem_scg(name, max_it):
         n = min(int(scg.stats["MaxIt"]), int(st["MaxIt"][p]))
         ref, new = scg.stats["fx"][:n], st["fx"][:n, p]
         assert np.max(np.abs(new - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-6, p
-        assert abs(int(scg.stats["MaxIt"]) - int(st["MaxIt"][p])) <= 2, p
+        # (a trace that ends in a bit-flat plateau stops where rounding decides: conftest.stop_tolerance)
+        n1 = int(scg.stats["MaxIt"])
+        assert abs(n1 - int(st["MaxIt"][p])) <= stop_tolerance(scg.stats["fx"][:n1], n1), p
         assert abs(fx[p] - f1) <= 1e-6 * max(abs(f1), 1.0), p
         assert np.abs(Xh[p] - x1).max() <= 1e-5 * max(np.abs(x1).max(), 1.0), p
         assert np.allclose(st["beta"][:n, p], scg.stats["beta"][:n])

@@ -863,15 +863,20 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
 }
 
 // The free energy of problem p from its Esde integrand f(t) and its moments (global or shared memory); every
-// thread of the 128-thread CTA calls it, every thread gets the value.  parts: E0, Esde, Eobs (or null).
+// thread of the CTA (128 threads or more) calls it, every thread gets the value.  parts: E0, Esde, Eobs (or null).
 __device__ __forceinline__ double free_energy_of(const Batch& b, int p, const double* f, const double* mt,
                                                  const double* st, double* sh, double* parts)
 {
+    // The partial sums are taken by the first 128 threads whatever the CTA size (the rest add zeros to the
+    // reduction tree), so that F is the same bits from finalize_kernel (128 threads) and from the fused D = 1
+    // evaluation (SCAN_THREADS).
+    constexpr int W = 128;
     const int tid = threadIdx.x;
     const int N = b.N, D = b.D, M = b.M, DD = D * D;
     // utilities.py:144-201: composite trapezoid, sum(dx * (f[i+1] + f[i]) / 2)
     double acc = 0.0;
-    for (int i = tid; i < N - 1; i += blockDim.x) acc += b.dt_model * (f[i + 1] + f[i]) / 2.0;
+    if (tid < W)
+        for (int i = tid; i < N - 1; i += W) acc += b.dt_model * (f[i + 1] + f[i]) / 2.0;
     double Esde = block_sum(acc, sh);
     if (b.model == MODEL_DW || b.model == MODEL_OU)  // double_well.py:217, ornstein_uhlenbeck.py:208
         Esde = 0.5 * Esde / b.sigma[p * b.sigma_stride];
@@ -882,7 +887,7 @@ __device__ __forceinline__ double free_energy_of(const Batch& b, int p, const do
     const double LOG2PI = 1.8378770664093453;
     if (D == 1) {  // gaussian_like.py:69-96
         acc = 0.0;
-        for (int n = tid; n < M; n += blockDim.x) {
+        for (int n = tid; n < (tid < W ? M : 0); n += W) {
             const long long t = b.obs_t[n];
             const double y = oy[n], E2 = mt[t] * mt[t] + st[t];
             acc += (y * y) - 2.0 * y * mt[t] + E2;
@@ -891,7 +896,7 @@ __device__ __forceinline__ double free_energy_of(const Batch& b, int p, const do
         Eobs = 0.5 * sm / R[0] + 0.5 * M * (LOG2PI + log(R[0]));
     } else {  // gaussian_like.py:98-153; S diagonal indexed by the observation ORDINAL n
         acc = 0.0;
-        for (int q = tid; q < M * D; q += blockDim.x) {
+        for (int q = tid; q < (tid < W ? M * D : 0); q += W) {
             const int n = q / D, i = q % D;
             const long long t = b.obs_t[n];
             const double z = (oy[(long long)n * D + i] - mt[t * D + i]) / sqrt(R[i]);
@@ -924,33 +929,33 @@ finalize_kernel(Batch b, Scratch s, double* __restrict__ F, int p0, int count, E
 }
 
 // ---------------------------------------------------------------------------
-// D = 1 (DW, OU), small batches: time-parallel sweeps, one 128-thread CTA per problem.
+// D = 1 (DW, OU): time-parallel sweeps, one CTA of SCAN_THREADS threads per problem.
 //
 // With one thread per problem the sweeps above are a chain of N-1 dependent solver steps (~450 cycles
 // each: OU x 1024, N = 1001 took 0.26 + 0.61 ms whatever the batch size).  But both moment ODEs are
 // LINEAR in their state -- m' = -A m + b, S' = -2 A S + sigma, lam' and Psi' likewise
 // (fwd_ode.py:41-75, bwd_ode.py:45-83) -- so one solver step is an affine map y -> P y + Q of each scalar,
 // whatever the solver (the one exception: RK2's forward variance stage, runge_kutta2.py:92, passes S in
-// place of A and is quadratic in S; that sweep stays sequential).  The CTA first stages the problem's
+// place of A and is quadratic in S; see scan1_fwd_body).  The CTA first stages the problem's
 // streams (A, b; backward also m, S, dE/dm, dE/dS) in shared memory with coalesced loads; then each thread
-// takes a contiguous run of ~(N-1)/128 steps and
+// takes a contiguous run of ~(N-1)/SCAN_THREADS steps and
 //   1. finds the (P, Q) of every step of its run by applying THE SOLVER STEP ITSELF (fwd_step / bwd_step,
 //      observation jumps included) to the states 0 and 1, and composes them;
 //   2. a block scan composes the runs, giving each thread the state at the start of its run;
 //   3. the thread walks its run again from that state with the solver step, storing m(t), S(t) (forward)
 //      or assembling dL/dA(t), dL/db(t) (backward) exactly as the sequential kernels do.
-// The chain is ~2 x 8 steps + the scan instead of 1000 steps, for ~3x the arithmetic.  Only the run-start
+// The chain is ~2 x 5 steps + the scan instead of 1000 steps, for ~3x the arithmetic.  Only the run-start
 // states differ from the sequential kernels (rounding of the composed maps, ~1e-16 relative per step);
 // inside a run the arithmetic is the sequential one.
 // ---------------------------------------------------------------------------
 constexpr int SCAN_MAX_BATCH = 16384;     // the separate sweeps (F only; RK2's backward sweep): above, one thread per problem
                                           // fills the FP64 pipe better.  The fused evaluation (scan1_eval_kernel) has no such
                                           // limit: measured faster than the sequential kernels at every batch size
-                                          // (OU rk4 x 65536: 4.21 against 4.51 ms)
+                                          // (OU rk4 x 65536: 3.21 against 4.51 ms)
 constexpr int SCAN_RK2_MAX_BATCH = 8192;  // RK2's forward sweep keeps one serial recurrence per problem (scan1_fwd_body): measured
                                           // against one thread per problem, OU rk2: 1024 problems 0.158 / 0.79 ms, 8192 1.00 / 1.11,
                                           // 16384 1.95 / 1.37, 65536 7.7 / 4.1
-constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_THREADS = 256;         // 128: same throughput, one problem 25 instead of 19 us (longer runs per thread)
 // VGPA_SEQUENTIAL_D1=1 in the environment: D = 1 batches take the one-thread-per-problem kernels whatever their size
 // (a diagnostic switch: A/B timings, and tests that compare the two kernel families on the same problems)
 static bool scan_disabled()
@@ -984,6 +989,14 @@ __device__ __forceinline__ Affine scan_exclusive(Affine f, Affine* sh)
     __syncthreads();
     return after(e, pre);
 }
+// Steps per thread.  ODD: thread r works on shared-memory doubles r L + j, and with an even L (8 for a grid of
+// 1001 points) the 32 lanes of a warp fall on 2 of the 16 double-wide banks -- ncu showed 79 % of the kernel's
+// shared-memory wavefronts were bank-conflict replays and the LSU pipe 87 % busy.  With an odd stride the lanes
+// of each half-warp hit 16 different banks; a few threads at the end of the CTA stay idle instead.
+__device__ __forceinline__ int run_length(int steps)
+{
+    return ((steps + SCAN_THREADS - 1) / SCAN_THREADS) | 1;
+}
 __device__ __forceinline__ void stage_array(double* __restrict__ dst, const double* __restrict__ src, int n)
 {
     for (int i = threadIdx.x; i < n; i += SCAN_THREADS) dst[i] = __ldg(src + i);
@@ -1003,7 +1016,7 @@ __device__ __forceinline__ void scan1_fwd_body(const double* A, const double* bo
 {
     __shared__ double run_start[SCAN_THREADS];
     const int tid = threadIdx.x;
-    const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int steps = N - 1, L = run_length(steps);
     const int k0 = min(tid * L, steps), k1 = min(k0 + L, steps);
     const double zero = 0.0, one = 1.0, minus = -1.0;
     Affine fm{1.0, 0.0}, fS{1.0, 0.0};
@@ -1069,7 +1082,7 @@ __device__ __forceinline__ void scan1_bwd_body(const Batch& b, int p, const doub
     const double isg = 1.0 / b.sigma[p * b.sigma_stride], Rv = b.R[p * b.R_stride];
     const double dt = b.dt, dtm = b.dt_model;
     // step q = 0 .. N-2 takes index t = N-1-q to t-1
-    const int steps = N - 1, L = (steps + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int steps = N - 1, L = run_length(steps);
     const int q0 = min(tid * L, steps), q1 = min(q0 + L, steps);
     const double zero = 0.0, one = 1.0;
 
