@@ -124,6 +124,9 @@ int vgpa_set_active_list(vgpa_handle *h, const int32_t *list, int32_t n);
  * Same evaluation with DEVICE buffers on `stream` (a cudaStream_t passed as
  * void*; NULL = default stream).  Asynchronous: returns after enqueueing.
  * Call vgpa_sync to wait and to collect the positive-definiteness status.
+ * A handle owns one scratch: an evaluation enqueued on another stream than the
+ * previous one is ordered after it (an event wait on the device, no host
+ * synchronisation); for evaluations that should overlap use one handle each.
  */
 int vgpa_eval_device(vgpa_handle *h, const double *d_x, int64_t x_stride, int want_grad,
                      double *d_F, double *d_grad, int64_t grad_stride, void *stream);

@@ -124,6 +124,32 @@ def test_device_pointer_entry_point_matches_host_entry_point():
     assert np.array_equal(Fd.cpu().numpy(), F_h) and np.array_equal(Gd.cpu().numpy(), G_h)
 
 
+def test_device_evaluations_on_two_streams_share_one_handle_safely():
+    """A handle owns one scratch: two vgpa_eval_device calls enqueued back to back on DIFFERENT streams must not
+    overlap (the second waits for the first on the device), so both return what a lone evaluation returns."""
+    import torch
+    g = _load("eval_L96_rk2")
+    B = 6
+    rng = np.random.default_rng(19)
+    Xa = np.stack([g["x"] * (1.0 + 0.01 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    Xb = np.stack([g["x"] * (1.0 + 0.01 * rng.standard_normal(g["x"].size)) for _ in range(B)])
+    _, ev = _problem_and_evaluator(g, B=B)
+    with ev:
+        Fa_h, Ga_h = ev.eval(Xa)
+        Fb_h, Gb_h = ev.eval(Xb)
+        dev = [(torch.from_numpy(X).cuda(), torch.empty(B, dtype=torch.float64, device="cuda")) for X in (Xa, Xb)]
+        grads = [torch.empty_like(d[0]) for d in dev]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        torch.cuda.synchronize()
+        for rep in range(3):                      # alternate the streams a few times
+            for (Xd, Fd), Gd, s in zip(dev, grads, streams):
+                ev.eval_device(Xd.data_ptr(), ev.n_x, Fd.data_ptr(), Gd.data_ptr(), ev.n_x, s.cuda_stream)
+        ev.sync()
+        torch.cuda.synchronize()
+    assert np.array_equal(dev[0][1].cpu().numpy(), Fa_h) and np.array_equal(grads[0].cpu().numpy(), Ga_h)
+    assert np.array_equal(dev[1][1].cpu().numpy(), Fb_h) and np.array_equal(grads[1].cpu().numpy(), Gb_h)
+
+
 def test_misaligned_device_buffers_are_rejected():
     import torch
     g = _load("eval_L96_rk2")

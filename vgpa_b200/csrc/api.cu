@@ -58,6 +58,7 @@ struct vgpa_handle {
     int lanes = 1;
     cudaStream_t s_lane[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done = nullptr;      // end of the last vgpa_eval_device (a call on ANOTHER stream waits for it: one scratch)
     // host-API staging: two slots of one chunk each
     DevBuf st_x[2], st_g[2], st_F;
     DevBuf plist2[2];                   // vgpa_set_active_list: compacted list of problem indices (device copies,
@@ -426,6 +427,7 @@ void vgpa_destroy(vgpa_handle* h)
         if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -445,6 +447,10 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
         return h->fail(VGPA_EINVAL, "device buffers must be 16-byte aligned with even strides");
     CK(cudaSetDevice(h->d.device), "cudaSetDevice");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // The handle owns ONE scratch and one set of status words: an evaluation enqueued on another stream than the
+    // previous one is ordered after it (same stream: stream order does it).
+    if (h->ev_done != nullptr && h->status_dirty && st != h->last_stream)
+        CK(cudaStreamWaitEvent(st, h->ev_done, 0), "cudaStreamWaitEvent");
     CK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * h->d.B, st), "cudaMemsetAsync(status)");
     Extra ex{};
     const int total = (h->n_list >= 0 && h->batch.plist != nullptr) ? h->n_list : h->d.B;   // launch positions
@@ -474,6 +480,8 @@ int vgpa_eval_device(vgpa_handle* h, const double* d_x, int64_t x_stride, int wa
         CK(cudaEventRecord(h->plist_ev[q], st), "cudaEventRecord");
         h->plist_used[q] = true;
     }
+    if (h->ev_done == nullptr) CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaEventRecord(h->ev_done, st), "cudaEventRecord");
     h->last_stream = st;
     h->status_dirty = true;
     return VGPA_OK;
