@@ -374,6 +374,13 @@ def ensemble_scg(torch, dist, dev, local, rank, world, fam, per_gpu):
             p1 = min(hi - lo, p0 + 64)
             u = torch.rand((p1 - p0, N_X), dtype=torch.float64, device=dev, generator=gen) * 2.0 - 1.0
             X[p0:p1] = x0s[torch.from_numpy(iset[a + p0:a + p1]).to(dev)] * (1.0 + 0.02 * u)
+    # warm-up: two iterations of the first few members of each shard (lazily loaded modules, the first NCCL gather)
+    nw = min(per_gpu, 8)
+    shift = rank * (per_gpu - nw)            # warm-up problem k of this rank = problem k + shift of the real numbering
+    warm = ShardedBatchedSCG(nw * world, lambda lo, hi: make(lo + shift, hi + shift),
+                             {"max_it": 2, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False}, rank=rank, world=world)
+    warm.run(x0_fn=lambda lo, hi, X: x0_fn(lo + shift, hi + shift, X))
+    del warm
     ens = ShardedBatchedSCG(per_gpu * world, make, {"max_it": 500, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False},
                             rank=rank, world=world)
     torch.cuda.synchronize()
@@ -382,6 +389,7 @@ def ensemble_scg(torch, dist, dev, local, rank, world, fam, per_gpu):
     t0 = time.perf_counter()
     res = ens.run(x0_fn=x0_fn)
     torch.cuda.synchronize()
+    print(f"[ensemble_scg] rank {rank}: {time.perf_counter() - t0:.3f} s, phases {res['rank_phase_seconds']}", file=sys.stderr, flush=True)
     el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     useful = torch.tensor([float(res["f_eval"][rank * per_gpu:(rank + 1) * per_gpu].sum())], dtype=torch.float64, device=dev)
     if world > 1:
@@ -391,6 +399,7 @@ def ensemble_scg(torch, dist, dev, local, rank, world, fam, per_gpu):
     assert np.all(np.isfinite(res["fx"]))
     return {"optimisations_per_s": per_gpu * world / el, "problems": per_gpu * world, "problems_per_gpu": per_gpu,
             "seconds": el, "optimise_seconds_rank0": round(float(res["rank_optimise_seconds"]), 3),
+            "phase_seconds_rank0": res["rank_phase_seconds"],
             "iterations_min_median_max": [int(res["n_it"].min()), int(np.median(res["n_it"])), int(res["n_it"].max())],
             "f_evaluations_per_s": float(useful.item()) / el,
             "resident_sub_batch": int(res["sub_batch"]), "device_buffers_per_problem": 5,

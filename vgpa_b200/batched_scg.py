@@ -376,38 +376,49 @@ class ShardedBatchedSCG:
 
         def work(rng_):
             lo_, hi_ = rng_
+            t_create = time.perf_counter()
             ev = self.make_evaluator(lo_, hi_)
+            t_create = time.perf_counter() - t_create
             dev = torch.device("cuda", ev.device)
             torch.cuda.set_device(dev)
             stream = torch.cuda.Stream(dev) if concurrent > 1 else torch.cuda.current_stream(dev)
             try:
                 with torch.cuda.stream(stream):
                     b = ev.B
+                    t_x0 = time.perf_counter()
                     X = torch.empty((b, ev.n_x), dtype=torch.float64, device=dev)
                     if x0_fn is None:
                         ev.initialization_device(X.data_ptr(), ev.n_x, float(t0), stream.cuda_stream)
                         ev.sync()
                     else:
                         x0_fn(lo_, hi_, X)
+                    stream.synchronize()
+                    t_x0 = time.perf_counter() - t_x0
                     opt = BatchedSCG(ev, self.options)
                     t_opt = time.perf_counter()
                     Xf, fxb = opt(X, adopt=True)
                     stream.synchronize()
                     t_opt = time.perf_counter() - t_opt
-                    res = {"range": rng_, "optimise_seconds": t_opt, "fx": fxb, "n_it": opt.stats["MaxIt"], "f_eval": opt.stats["f_eval"],
+                    res = {"range": rng_, "optimise_seconds": t_opt, "create_seconds": t_create, "x0_seconds": t_x0, "fx": fxb, "n_it": opt.stats["MaxIt"], "f_eval": opt.stats["f_eval"],
                            "evaluations": opt.stats["evaluations"] * b, "syncs": opt.host_syncs,
                            "kept": {k: Xf[k - lo_].cpu().numpy() for k in keep if lo_ <= k < hi_}}
+                    t_free = time.perf_counter()
                     del opt, Xf, X
                 return res
             finally:
                 ev.close()
+                if "res" in locals():
+                    res["free_seconds"] = time.perf_counter() - t_free
 
         t_ = time.perf_counter()
+        t_cache = 0.0
         if concurrent == 1 or len(ranges) <= 1:
             results = []
             for r_ in ranges:
                 results.append(work(r_))
+                tc = time.perf_counter()
                 torch.cuda.empty_cache()
+                t_cache += time.perf_counter() - tc
         else:
             from concurrent.futures import ThreadPoolExecutor
             with ThreadPoolExecutor(max_workers=concurrent) as pool:
@@ -416,13 +427,15 @@ class ShardedBatchedSCG:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         seconds = time.perf_counter() - t_
-        evaluations, syncs, optimise_seconds = 0, 0, 0.0
+        evaluations, syncs, optimise_seconds, create_seconds, x0_seconds = 0, 0, 0.0, 0.0, 0.0
         for r in results:
             sl = slice(r["range"][0] - self.lo, r["range"][1] - self.lo)
             fx[sl], n_it[sl], f_eval[sl] = r["fx"], r["n_it"], r["f_eval"]
             evaluations += r["evaluations"]
             syncs += r["syncs"]
             optimise_seconds += r["optimise_seconds"]
+            create_seconds += r["create_seconds"]
+            x0_seconds += r["x0_seconds"]
             kept.update(r["kept"])
         # gather of the per-problem results (the only collective)
         def gather(v):
@@ -430,9 +443,15 @@ class ShardedBatchedSCG:
                 return v
             from .ensemble import gather_free_energies
             return gather_free_energies(np.asarray(v, dtype=np.float64), self.total, self.group)
+        t_g = time.perf_counter()
         out = {"fx": gather(fx), "n_it": gather(n_it.astype(np.float64)).astype(np.int64), "f_eval": gather(f_eval),
                "rank_seconds": seconds, "rank_optimise_seconds": optimise_seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
                "sub_batch": sub, "concurrent": concurrent, "kept": kept}
+        out["rank_phase_seconds"] = {"create_evaluators": round(create_seconds, 4), "starting_points": round(x0_seconds, 4),
+                                     "optimise": round(optimise_seconds, 4), "whole_loop": round(seconds, 4),
+                                     "close_evaluators": round(sum(r.get("free_seconds", 0.0) for r in results), 4),
+                                     "empty_cache": round(t_cache, 4),
+                                     "gather": round(time.perf_counter() - t_g, 4)}
         self.result = out
         return out
 
