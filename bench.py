@@ -541,6 +541,32 @@ def secondary_configs(torch, local, hbm_peak, with_reference=True):
         except Exception as e:   # the reference is optional here (numba / scipy missing on the box)
             out["DW_single_problem"]["reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
 
+    # configs[2], the single problem: one Lorenz-63 T=2000 RK2 problem through VarGP, and its whole SCG optimisation
+    sim = Simulation("bench")
+    sim.setup(base("L63", "RK2", 20.0, [10.0] * 3, 2.0, 5, [10.0, 28.0, 2.6667]))
+    v = sim.build()
+    x0 = v.initialization()
+    rng = np.random.default_rng(1)
+    xs = [x0 * (1.0 + 1e-3 * rng.uniform(-1, 1, x0.size)) for _ in range(4)]
+    for x_ in xs:
+        v.free_energy(x_)
+        v.gradient(x_)
+    ts = []
+    for i in range(20):
+        t0 = time.perf_counter()
+        v.free_energy(xs[i % 4])
+        v.gradient(xs[i % 4])
+        ts.append(time.perf_counter() - t0)
+    scg = SCG(v.free_energy, v.gradient, {"max_it": 500, "x_tol": 1.0e-6, "f_tol": 1.0e-8, "display": False})
+    t0 = time.perf_counter()
+    _, fx = scg(x0.copy())
+    el = time.perf_counter() - t0
+    out["L63_single_problem"] = {"pair_ms_median": round(1e3 * float(np.median(ts)), 3), "scg_seconds": round(el, 3),
+                                 "scg_iterations": int(scg.stats["MaxIt"]), "fx": float(fx),
+                                 "bound": "latency (16 lanes per problem, 2 x 2001 dependent solver steps)",
+                                 "through": "VarGP.free_energy + VarGP.gradient / SCG, host numpy in and out"}
+    v.close()
+
     # configs[3]: one L96 D=40 T=1000 problem -- latency bound by 2 x T x stages dependent products
     sim = Simulation("bench")
     sim.setup(l96_params())
