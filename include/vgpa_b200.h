@@ -264,6 +264,14 @@ int vgpa_bcopy(int B, int64_t n, const int32_t *mask, const double *src, double 
 int vgpa_bstats(int B, int64_t n, const double *x, int64_t stride, double *out2B, const int32_t *active,
                 void *stream);
 
+/* Hand-over of the trajectory scratch between handles.  enable != 0: from now on the large device blocks of a
+ * destroyed handle are kept and given to the next vgpa_create that needs exactly the same sizes on the same
+ * device (an ensemble processed in sub-batches of one shape: no cudaFree / cudaMalloc of tens of GB per
+ * sub-batch; cudaFree was measured at up to 2 s when several processes free at once).  enable == 0: switch it
+ * off and free what is kept; returns the bytes released.  Kept blocks are also released when an allocation of
+ * this library would otherwise fail.  Off by default.  Thread-safe. */
+long long vgpa_scratch_cache(int enable);
+
 /* Per-kernel device timing for bench.py's roofline: when enabled, every kernel
  * launch of vgpa_eval / vgpa_eval_device is bracketed by CUDA events on the
  * launching stream.  vgpa_get_timing synchronises, then returns the accumulated

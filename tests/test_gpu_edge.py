@@ -150,6 +150,38 @@ def test_device_evaluations_on_two_streams_share_one_handle_safely():
     assert np.array_equal(dev[1][1].cpu().numpy(), Fb_h) and np.array_equal(grads[1].cpu().numpy(), Gb_h)
 
 
+def test_scratch_hand_over_between_handles():
+    """vgpa_scratch_cache: with the hand-over on, the scratch of a destroyed handle is kept (free device memory
+    does not come back) and serves the next handle of the same shape; switching it off releases it; results are
+    those of a fresh handle either way."""
+    import torch
+    from vgpa_b200._lib import lib
+    g = _load("eval_L96_rk2")
+    B = 200                                   # S(t) and dE/dS scratch of ~54 MB each: above the 32 MB threshold
+    X = g["x"]                                # one x shared by all problems
+    _, ev = _problem_and_evaluator(g, B=B)
+    with ev:
+        F0, G0 = ev.eval(X)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    assert lib.vgpa_scratch_cache(1) == 0
+    try:
+        _, ev = _problem_and_evaluator(g, B=B)
+        with ev:
+            F1, G1 = ev.eval(X)
+        kept = free0 - torch.cuda.mem_get_info()[0]
+        assert kept > (32 << 20)                             # the closed handle's scratch is still ours
+        _, ev = _problem_and_evaluator(g, B=B)               # same shape: served from the kept blocks
+        with ev:
+            assert free0 - torch.cuda.mem_get_info()[0] <= kept + (64 << 20)
+            F2, G2 = ev.eval(X)
+    finally:
+        released = lib.vgpa_scratch_cache(0)
+    assert released >= kept - (64 << 20) and released > 0
+    assert free0 - torch.cuda.mem_get_info()[0] < (64 << 20)
+    assert np.array_equal(F1, F0) and np.array_equal(G1, G0) and np.array_equal(F2, F0) and np.array_equal(G2, G0)
+
+
 def test_misaligned_device_buffers_are_rejected():
     import torch
     g = _load("eval_L96_rk2")

@@ -91,6 +91,8 @@ def _load():
         fn.argtypes = args
     lib.vgpa_host_alloc.restype = C.c_void_p
     lib.vgpa_host_alloc.argtypes = [C.c_int64]
+    lib.vgpa_scratch_cache.restype = C.c_longlong
+    lib.vgpa_scratch_cache.argtypes = [C.c_int]
     lib.vgpa_host_free.restype = None
     lib.vgpa_host_free.argtypes = [C.c_void_p]
     lib.vgpa_host_copy.restype = None

@@ -306,6 +306,26 @@ def save_ensemble(name, output):
     return out
 
 
+_release_thread = None
+
+
+def _start_release():
+    """Switch the scratch hand-over off and free what it still holds, on a background thread."""
+    global _release_thread
+    import threading
+    _join_release()
+    _release_thread = threading.Thread(target=lib.vgpa_scratch_cache, args=(0,), name="vgpa-scratch-release")
+    _release_thread.start()
+
+
+def _join_release():
+    """Wait for a release still in flight (its memory is about to be needed)."""
+    global _release_thread
+    if _release_thread is not None:
+        _release_thread.join()
+        _release_thread = None
+
+
 class ShardedBatchedSCG:
     """An ensemble of `total` independent optimisations over the GPUs of one node (one process per GPU,
     contiguous blocks of problems as in vgpa_b200.ensemble) in device-resident sub-batches: per sub-batch
@@ -410,20 +430,30 @@ class ShardedBatchedSCG:
                 if "res" in locals():
                     res["free_seconds"] = time.perf_counter() - t_free
 
+        # Evaluators of one shape follow each other: the library hands the scratch of a closed one to the next
+        # (vgpa_scratch_cache) instead of freeing and re-allocating tens of GB per sub-batch.  What is still kept
+        # at the end is released on a background thread: the results are complete, and a cudaFree of that size
+        # takes up to seconds when every rank of a node frees at the same time.
+        _join_release()
+        lib.vgpa_scratch_cache(1)
         t_ = time.perf_counter()
         t_cache = 0.0
-        if concurrent == 1 or len(ranges) <= 1:
-            results = []
-            for r_ in ranges:
-                results.append(work(r_))
-                tc = time.perf_counter()
+        try:
+            if concurrent == 1 or len(ranges) <= 1:
+                results = []
+                for r_ in ranges:
+                    results.append(work(r_))
+                    tc = time.perf_counter()
+                    torch.cuda.empty_cache()
+                    t_cache += time.perf_counter() - tc
+            else:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=concurrent) as pool:
+                    results = list(pool.map(work, ranges))
                 torch.cuda.empty_cache()
-                t_cache += time.perf_counter() - tc
-        else:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=concurrent) as pool:
-                results = list(pool.map(work, ranges))
-            torch.cuda.empty_cache()
+        except BaseException:
+            lib.vgpa_scratch_cache(0)
+            raise
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         seconds = time.perf_counter() - t_
@@ -443,6 +473,7 @@ class ShardedBatchedSCG:
                 return v
             from .ensemble import gather_free_energies
             return gather_free_energies(np.asarray(v, dtype=np.float64), self.total, self.group)
+        _start_release()
         t_g = time.perf_counter()
         out = {"fx": gather(fx), "n_it": gather(n_it.astype(np.float64)).astype(np.int64), "f_eval": gather(f_eval),
                "rank_seconds": seconds, "rank_optimise_seconds": optimise_seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
@@ -451,6 +482,7 @@ class ShardedBatchedSCG:
                                      "optimise": round(optimise_seconds, 4), "whole_loop": round(seconds, 4),
                                      "close_evaluators": round(sum(r.get("free_seconds", 0.0) for r in results), 4),
                                      "empty_cache": round(t_cache, 4),
+                                     "scratch_release": "on a background thread after the results (vgpa_scratch_cache)",
                                      "gather": round(time.perf_counter() - t_g, 4)}
         self.result = out
         return out
