@@ -309,12 +309,20 @@ def save_ensemble(name, output):
 _release_thread = None
 
 
+def _release_now():
+    """Switch the scratch hand-over off, free what it still holds and what torch's allocator caches."""
+    import torch
+    lib.vgpa_scratch_cache(0)
+    torch.cuda.empty_cache()
+
+
 def _start_release():
-    """Switch the scratch hand-over off and free what it still holds, on a background thread."""
+    """_release_now on a background thread: tens of GB of cudaFree take up to seconds when every rank of a node
+    frees at the same time, and nothing the caller is waiting for depends on it."""
     global _release_thread
     import threading
     _join_release()
-    _release_thread = threading.Thread(target=lib.vgpa_scratch_cache, args=(0,), name="vgpa-scratch-release")
+    _release_thread = threading.Thread(target=_release_now, name="vgpa-scratch-release")
     _release_thread.start()
 
 
@@ -431,28 +439,34 @@ class ShardedBatchedSCG:
                     res["free_seconds"] = time.perf_counter() - t_free
 
         # Evaluators of one shape follow each other: the library hands the scratch of a closed one to the next
-        # (vgpa_scratch_cache) instead of freeing and re-allocating tens of GB per sub-batch.  What is still kept
-        # at the end is released on a background thread: the results are complete, and a cudaFree of that size
-        # takes up to seconds when every rank of a node frees at the same time.
+        # (vgpa_scratch_cache) instead of freeing and re-allocating tens of GB per sub-batch, and torch's allocator
+        # does the same for the optimiser's buffers.  What is still kept at the end is released on a background
+        # thread AFTER the gather: the results are complete, and a cudaFree of that size takes up to seconds when
+        # every rank of a node frees at the same time (a release started before the gather only made the gather
+        # wait for it: measured).
         _join_release()
         lib.vgpa_scratch_cache(1)
         t_ = time.perf_counter()
-        t_cache = 0.0
+        def work_retry(rng_):
+            # Sub-batches of one shape reuse the torch allocator's cached buffers and the library's kept scratch.
+            # When the shape changes (the last, smaller sub-batch) what is kept may be in the way: release, retry.
+            try:
+                return work(rng_)
+            except torch.cuda.OutOfMemoryError:
+                lib.vgpa_scratch_cache(0)
+                torch.cuda.empty_cache()
+                lib.vgpa_scratch_cache(1)
+                return work(rng_)
+
         try:
             if concurrent == 1 or len(ranges) <= 1:
-                results = []
-                for r_ in ranges:
-                    results.append(work(r_))
-                    tc = time.perf_counter()
-                    torch.cuda.empty_cache()
-                    t_cache += time.perf_counter() - tc
+                results = [work_retry(r_) for r_ in ranges]
             else:
                 from concurrent.futures import ThreadPoolExecutor
                 with ThreadPoolExecutor(max_workers=concurrent) as pool:
-                    results = list(pool.map(work, ranges))
-                torch.cuda.empty_cache()
+                    results = list(pool.map(work_retry, ranges))
         except BaseException:
-            lib.vgpa_scratch_cache(0)
+            _release_now()
             raise
         if torch.cuda.is_available():
             torch.cuda.synchronize()
@@ -473,7 +487,6 @@ class ShardedBatchedSCG:
                 return v
             from .ensemble import gather_free_energies
             return gather_free_energies(np.asarray(v, dtype=np.float64), self.total, self.group)
-        _start_release()
         t_g = time.perf_counter()
         out = {"fx": gather(fx), "n_it": gather(n_it.astype(np.float64)).astype(np.int64), "f_eval": gather(f_eval),
                "rank_seconds": seconds, "rank_optimise_seconds": optimise_seconds, "rank_problem_evaluations": evaluations, "rank_host_syncs": syncs,
@@ -481,10 +494,10 @@ class ShardedBatchedSCG:
         out["rank_phase_seconds"] = {"create_evaluators": round(create_seconds, 4), "starting_points": round(x0_seconds, 4),
                                      "optimise": round(optimise_seconds, 4), "whole_loop": round(seconds, 4),
                                      "close_evaluators": round(sum(r.get("free_seconds", 0.0) for r in results), 4),
-                                     "empty_cache": round(t_cache, 4),
-                                     "scratch_release": "on a background thread after the results (vgpa_scratch_cache)",
+                                     "release": "scratch (vgpa_scratch_cache) and torch cache: on a background thread, after the gather",
                                      "gather": round(time.perf_counter() - t_g, 4)}
         self.result = out
+        _start_release()
         return out
 
     def save(self, name, N, D):
